@@ -1,0 +1,75 @@
+# nsparse-b200 build.  Targets keep the names of the reference cuda-c/Makefile where they overlap
+# (spgemm_hash_s/d, amb_s/d); the sample drivers are compiled UNCHANGED from the reference tree when
+# it is present (REF_DIR), against include/nsparse.h and libnsparse_{s,d}.a.
+NVCC      ?= nvcc
+CXX       := /usr/bin/g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fopenmp --expt-extended-lambda -Iinclude
+REF_DIR   ?= /root/reference
+SRC       := nsparse_b200/csrc
+OBJ       := build/obj
+LIBDIR    := nsparse_b200/lib
+BIN       := bin
+
+CORE_CU   := context spgemm_plan spgemm_symbolic spgemm_numeric_s spgemm_numeric_d c_api
+CORE_OBJ  := $(addprefix $(OBJ)/,$(addsuffix .o,$(CORE_CU))) $(OBJ)/gen.o
+
+.PHONY: all lib compat drivers clean oracle
+all: lib compat oracle
+
+lib: $(LIBDIR)/libnsparse_b200.so
+
+$(OBJ)/%.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h $(SRC)/*.cuh include/*.h)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(OBJ)/gen.o: $(SRC)/gen.cpp include/nsparse_b200.h
+	@mkdir -p $(OBJ)
+	$(CXX) -O3 -fPIC -fopenmp -Iinclude -c $< -o $@
+
+$(LIBDIR)/libnsparse_b200.so: $(CORE_OBJ)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared -o $@ $^ -Xcompiler -fopenmp -lcudart -lgomp
+
+# ---- the nsparse.h API, one archive per precision (reference: .s.o / .d.o objects) ----
+compat: $(LIBDIR)/libnsparse_s.a $(LIBDIR)/libnsparse_d.a
+
+$(OBJ)/compat_api.s.o: $(SRC)/compat_api.cu $(wildcard $(SRC)/*.h $(SRC)/*.cuh include/*.h)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -DFLOAT -c $< -o $@
+$(OBJ)/compat_api.d.o: $(SRC)/compat_api.cu $(wildcard $(SRC)/*.h $(SRC)/*.cuh include/*.h)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -DDOUBLE -c $< -o $@
+$(OBJ)/compat_cusparse.s.o: $(SRC)/compat_cusparse.cu include/nsparse.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -DFLOAT -c $< -o $@
+$(OBJ)/compat_cusparse.d.o: $(SRC)/compat_cusparse.cu include/nsparse.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -DDOUBLE -c $< -o $@
+
+$(LIBDIR)/libnsparse_s.a: $(OBJ)/compat_api.s.o $(OBJ)/compat_cusparse.s.o $(CORE_OBJ)
+	@mkdir -p $(LIBDIR)
+	rm -f $@ && ar rcs $@ $^
+$(LIBDIR)/libnsparse_d.a: $(OBJ)/compat_api.d.o $(OBJ)/compat_cusparse.d.o $(CORE_OBJ)
+	@mkdir -p $(LIBDIR)
+	rm -f $@ && ar rcs $@ $^
+
+# ---- unchanged reference sample drivers (only when the reference tree is mounted) ----
+DRV_FLAGS := $(ARCH) -O3 -Iinclude -Wno-deprecated-declarations -Xcompiler -fopenmp
+drivers: compat
+	@mkdir -p $(BIN)
+	@if [ -d $(REF_DIR)/cuda-c/src/sample ]; then \
+	  set -e; \
+	  $(NVCC) $(DRV_FLAGS) -DFLOAT  $(REF_DIR)/cuda-c/src/sample/spgemm/spgemm_hash.cu -o $(BIN)/spgemm_hash_s -L$(LIBDIR) -lnsparse_s -lcusparse -lgomp; \
+	  $(NVCC) $(DRV_FLAGS) -DDOUBLE $(REF_DIR)/cuda-c/src/sample/spgemm/spgemm_hash.cu -o $(BIN)/spgemm_hash_d -L$(LIBDIR) -lnsparse_d -lcusparse -lgomp; \
+	  $(NVCC) $(DRV_FLAGS) -DFLOAT  $(REF_DIR)/cuda-c/src/sample/spmv/spmv_amb.cu -o $(BIN)/amb_s -L$(LIBDIR) -lnsparse_s -lcusparse -lgomp; \
+	  $(NVCC) $(DRV_FLAGS) -DDOUBLE $(REF_DIR)/cuda-c/src/sample/spmv/spmv_amb.cu -o $(BIN)/amb_d -L$(LIBDIR) -lnsparse_d -lcusparse -lgomp; \
+	  echo "drivers built from $(REF_DIR) (sources unchanged)"; \
+	else echo "reference tree not present: drivers skipped"; fi
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -rf build $(LIBDIR) $(BIN)
+	$(MAKE) -C oracle clean

@@ -1,0 +1,168 @@
+/*
+ * nsparse_b200.h -- plain C ABI of libnsparse_b200.so
+ *
+ * extern "C", raw pointers and sizes only; no torch / C++ types.  This is what a
+ * binding (ctypes in nsparse_b200/_lib.py, cgo, JNI ...) loads.  Every entry point
+ * names the reference interface it replaces (paths relative to the nsparse tree).
+ *
+ * Conventions
+ *   - all functions return 0 on success, a negative nsp_status otherwise;
+ *     nsp_last_error() gives the message of the last failure on that context.
+ *   - "d_" arguments are DEVICE pointers on the context's GPU, "h_" are HOST pointers.
+ *   - CSR is 0-based; rpt of the INPUTS is int32 (nnz < 2^31, like sfCSR); the row
+ *     pointer of the PRODUCT is int64 because C = A*A of an R-MAT scale-20 graph has
+ *     ~9e9 entries, which sfCSR's `int nnz` (nsparse.h:62-75) cannot hold.
+ *     nsp_rpt64_to_rpt32() narrows it for callers that keep the sfCSR layout.
+ *   - calls are asynchronous on the context's stream unless they return a host scalar
+ *     (nnz, flop); nsp_sync() joins.
+ */
+#ifndef NSPARSE_B200_C_ABI_H
+#define NSPARSE_B200_C_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nsp_context nsp_context;
+
+typedef enum {
+    NSP_OK = 0,
+    NSP_ERR_CUDA = -1,        /* a CUDA runtime call failed                          */
+    NSP_ERR_ARG = -2,         /* bad argument                                        */
+    NSP_ERR_OVERFLOW = -3,    /* result does not fit the requested index width       */
+    NSP_ERR_NOMEM = -4
+} nsp_status;
+
+/* ------------------------------------------------------------------------------------
+ * context: device, stream, grow-only workspace arena.  Replaces the per-call
+ * init_bin/release_bin (kernel_spgemm_hash_d.cu:33-68: 7 cudaStreamCreate + 5 cudaMalloc
+ * per SpGEMM) with state that is created once.
+ * ---------------------------------------------------------------------------------- */
+int nsp_create(nsp_context **ctx, int device);
+int nsp_destroy(nsp_context *ctx);
+const char *nsp_last_error(nsp_context *ctx);
+/* stream == NULL selects the legacy default stream (what the sample drivers time on). */
+int nsp_set_stream(nsp_context *ctx, void *cuda_stream);
+int nsp_sync(nsp_context *ctx);
+/* tuning knobs, mostly for tests: name in {"sym_bitmap_min", "num_bitmap_min", "lanes_per_brow"} */
+int nsp_set_option(nsp_context *ctx, const char *name, long long value);
+/* number of kernels this library launched on the context since creation (bench.py: gpu_launches) */
+long long nsp_launch_count(nsp_context *ctx);
+
+/* ------------------------------------------------------------------------------------
+ * hash SpGEMM, C = A * B       A: M x K,  B: K x N,  C: M x N
+ * ---------------------------------------------------------------------------------- */
+
+/* get_spgemm_flop (kernel_spgemm_cu_csr.cu:35-57): flop = 2 * sum_i sum_{j in A_i} nnz(B_j). */
+int nsp_spgemm_flop(nsp_context *ctx, int M,
+                    const int *d_a_rpt, const int *d_a_col, const int *d_b_rpt,
+                    long long *h_flop);
+
+/* Symbolic phase = init_bin + set_max_bin + set_row_nnz (kernel_spgemm_hash_d.cu:33-198,
+ * 1077-1185).  Writes the exclusive row pointer of C (int64, M+1 entries) and returns
+ * nnz(C) and the number of intermediate products.  Synchronises (nnz is needed to
+ * allocate C, as in the reference :1184). */
+int nsp_spgemm_symbolic(nsp_context *ctx, int M, int K, int N,
+                        const int *d_a_rpt, const int *d_a_col,
+                        const int *d_b_rpt, const int *d_b_col,
+                        long long *d_c_rpt64,
+                        long long *h_nnz_c, long long *h_intprod);
+
+/* Numeric phase = set_min_bin + calculate_value_col_bin (kernel_spgemm_hash_d.cu:201-246,
+ * 1187-1288).  d_c_col / d_c_val must hold nnz(C) entries.  Rows of C come out with
+ * ascending column indices; numerical zeros are kept (structural product).
+ * Must follow nsp_spgemm_symbolic on the same context with the same A, B. */
+int nsp_spgemm_numeric_s(nsp_context *ctx, int M, int K, int N,
+                         const int *d_a_rpt, const int *d_a_col, const float *d_a_val,
+                         const int *d_b_rpt, const int *d_b_col, const float *d_b_val,
+                         const long long *d_c_rpt64, int *d_c_col, float *d_c_val);
+int nsp_spgemm_numeric_d(nsp_context *ctx, int M, int K, int N,
+                         const int *d_a_rpt, const int *d_a_col, const double *d_a_val,
+                         const int *d_b_rpt, const int *d_b_col, const double *d_b_val,
+                         const long long *d_c_rpt64, int *d_c_col, double *d_c_val);
+
+/* Narrow an int64 row pointer to the int32 one sfCSR carries; NSP_ERR_OVERFLOW if
+ * nnz > INT_MAX (the reference silently wraps, kernel_spgemm_hash_d.cu:1183). */
+int nsp_rpt64_to_rpt32(nsp_context *ctx, int M, const long long *d_rpt64, long long nnz, int *d_rpt32);
+
+/* spgemm_kernel_hash (kernel_spgemm_hash_d.cu:1035-1075) with HOST buffers: copies A and
+ * B to the device, runs both phases and leaves C on the device inside the context.
+ * nsp_spgemm_host_fetch_* then copies C into caller-provided host arrays (any of the
+ * three may be NULL to skip it) and nsp_spgemm_host_release frees the device copy. */
+int nsp_spgemm_host_s(nsp_context *ctx, int M, int K, int N,
+                      const int *h_a_rpt, const int *h_a_col, const float *h_a_val,
+                      const int *h_b_rpt, const int *h_b_col, const float *h_b_val,
+                      long long *h_nnz_c);
+int nsp_spgemm_host_d(nsp_context *ctx, int M, int K, int N,
+                      const int *h_a_rpt, const int *h_a_col, const double *h_a_val,
+                      const int *h_b_rpt, const int *h_b_col, const double *h_b_val,
+                      long long *h_nnz_c);
+int nsp_spgemm_host_fetch_s(nsp_context *ctx, long long *h_c_rpt64, int *h_c_col, float *h_c_val);
+int nsp_spgemm_host_fetch_d(nsp_context *ctx, long long *h_c_rpt64, int *h_c_col, double *h_c_val);
+/* Streams C through a caller-provided (pinned) staging buffer of `stage_bytes` and folds it
+ * into a 64-bit checksum on the host; for results that do not fit host memory. */
+int nsp_spgemm_host_drain(nsp_context *ctx, void *h_stage, size_t stage_bytes,
+                          unsigned long long *h_checksum, long long *h_bytes);
+int nsp_spgemm_host_release(nsp_context *ctx);
+
+/* ------------------------------------------------------------------------------------
+ * AMB SpMV, y = A * x
+ * ---------------------------------------------------------------------------------- */
+
+/* Device part of sfAMB (nsparse.h:78-107); arrays are cudaMalloc'ed by nsp_csr2amb_*. */
+typedef struct {
+    int *d_cs;
+    unsigned int *d_cl;
+    unsigned short *d_sellcs_col;
+    void *d_sellcs_val;                 /* float* or double*                              */
+    unsigned short *d_s_write_permutation;
+    unsigned short *d_s_write_permutation_offset;
+    int *d_write_permutation;
+    int block_size;
+    int nnz;                            /* stored values incl. padding                    */
+    int M, N, pad_M;
+    int chunk;                          /* 32                                             */
+    int SIGMA;                          /* 32768                                          */
+    int c_size;                         /* non-empty chunks                               */
+    long long seg_size, seg_num;
+    long long thread_grid, thread_block;/* launch shape picked by the planner             */
+} nsp_amb;
+
+/* sf_csr2amb (convert_amb.cu:835-929).  seg_size == 0 / block_size == 0 ask the planner
+ * (footprint model of convert_amb.cu:785-797, optionally refined by timing when
+ * autotune != 0, which is what the reference's `AT` build does).  d_x is only read when
+ * autotune != 0. */
+int nsp_csr2amb_s(nsp_context *ctx, int M, int N, int nnz,
+                  const int *d_rpt, const int *d_col, const float *d_val,
+                  long long seg_size, int block_size, int autotune, const float *d_x,
+                  nsp_amb *out);
+int nsp_csr2amb_d(nsp_context *ctx, int M, int N, int nnz,
+                  const int *d_rpt, const int *d_col, const double *d_val,
+                  long long seg_size, int block_size, int autotune, const double *d_x,
+                  nsp_amb *out);
+int nsp_amb_free(nsp_context *ctx, nsp_amb *mat);
+
+/* sf_spmv_amb (kernel_spmv_amb.cu:98-104).  y[0..M) is overwritten.  x needs N entries
+ * (no padding is read), y needs M entries. */
+int nsp_spmv_amb_s(nsp_context *ctx, const nsp_amb *mat, const float *d_x, float *d_y);
+int nsp_spmv_amb_d(nsp_context *ctx, const nsp_amb *mat, const double *d_x, double *d_y);
+
+/* The same with HOST x / y (copies inside). */
+int nsp_spmv_amb_host_s(nsp_context *ctx, const nsp_amb *mat, const float *h_x, float *h_y);
+int nsp_spmv_amb_host_d(nsp_context *ctx, const nsp_amb *mat, const double *h_x, double *h_y);
+
+/* ------------------------------------------------------------------------------------
+ * synthetic inputs (host side, OpenMP; counter-based so every rank and the numpy mirror
+ * in nsparse_b200/gen.py produce identical edges)
+ * ---------------------------------------------------------------------------------- */
+/* Graph500 Kronecker edges, (a,b,c,d) = (0.57,0.19,0.19,0.05), no permutation, no noise. */
+int nsp_gen_rmat_edges(int scale, long long n_edges, unsigned long long seed,
+                       long long *h_src, long long *h_dst);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSPARSE_B200_C_ABI_H */

@@ -1,0 +1,290 @@
+// nsparse-b200: the extern "C" boundary (include/nsparse_b200.h).
+#include "../../include/nsparse_b200.h"
+
+#include <string.h>
+
+#include "context.h"
+
+using nsp::context_create;
+using nsp::context_destroy;
+
+#define NSP_REQUIRE_CTX(ctx) \
+    if (!(ctx)) return NSP_ERR_ARG; \
+    cudaSetDevice((ctx)->device)
+
+extern "C" {
+
+int nsp_create(nsp_context **ctx, int device) { return context_create(ctx, device); }
+int nsp_destroy(nsp_context *ctx) { return context_destroy(ctx); }
+const char *nsp_last_error(nsp_context *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int nsp_set_stream(nsp_context *ctx, void *cuda_stream)
+{
+    NSP_REQUIRE_CTX(ctx);
+    NSP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+int nsp_sync(nsp_context *ctx)
+{
+    NSP_REQUIRE_CTX(ctx);
+    NSP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int nsp_set_option(nsp_context *ctx, const char *name, long long value)
+{
+    if (!ctx || !name) return NSP_ERR_ARG;
+    if (!strcmp(name, "sym_bitmap_min")) ctx->opt_sym_bitmap_min = value;
+    else if (!strcmp(name, "num_bitmap_min")) ctx->opt_num_bitmap_min = value;
+    else if (!strcmp(name, "lanes_per_brow")) {
+        if (value != 0 && value != 4 && value != 8 && value != 16 && value != 32)
+            return ctx->fail(NSP_ERR_ARG, "lanes_per_brow must be 0, 4, 8, 16 or 32");
+        ctx->opt_lanes_per_brow = value;
+    } else
+        return ctx->fail(NSP_ERR_ARG, std::string("unknown option ") + name);
+    return 0;
+}
+
+long long nsp_launch_count(nsp_context *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- SpGEMM, device pointers ---------------------------------------------------------------
+int nsp_spgemm_flop(nsp_context *ctx, int M, const int *d_a_rpt, const int *d_a_col, const int *d_b_rpt,
+                    long long *h_flop)
+{
+    NSP_REQUIRE_CTX(ctx);
+    return nsp::spgemm_flop(ctx, M, d_a_rpt, d_a_col, d_b_rpt, h_flop);
+}
+
+int nsp_spgemm_symbolic(nsp_context *ctx, int M, int K, int N, const int *d_a_rpt, const int *d_a_col,
+                        const int *d_b_rpt, const int *d_b_col, long long *d_c_rpt64, long long *h_nnz_c,
+                        long long *h_intprod)
+{
+    NSP_REQUIRE_CTX(ctx);
+    return nsp::spgemm_symbolic(ctx, M, K, N, d_a_rpt, d_a_col, d_b_rpt, d_b_col, d_c_rpt64, h_nnz_c,
+                                h_intprod);
+}
+
+int nsp_spgemm_numeric_s(nsp_context *ctx, int M, int K, int N, const int *d_a_rpt, const int *d_a_col,
+                         const float *d_a_val, const int *d_b_rpt, const int *d_b_col, const float *d_b_val,
+                         const long long *d_c_rpt64, int *d_c_col, float *d_c_val)
+{
+    NSP_REQUIRE_CTX(ctx);
+    return nsp::spgemm_numeric<float>(ctx, M, K, N, d_a_rpt, d_a_col, d_a_val, d_b_rpt, d_b_col, d_b_val,
+                                      d_c_rpt64, d_c_col, d_c_val);
+}
+
+int nsp_spgemm_numeric_d(nsp_context *ctx, int M, int K, int N, const int *d_a_rpt, const int *d_a_col,
+                         const double *d_a_val, const int *d_b_rpt, const int *d_b_col,
+                         const double *d_b_val, const long long *d_c_rpt64, int *d_c_col, double *d_c_val)
+{
+    NSP_REQUIRE_CTX(ctx);
+    return nsp::spgemm_numeric<double>(ctx, M, K, N, d_a_rpt, d_a_col, d_a_val, d_b_rpt, d_b_col, d_b_val,
+                                       d_c_rpt64, d_c_col, d_c_val);
+}
+
+int nsp_rpt64_to_rpt32(nsp_context *ctx, int M, const long long *d_rpt64, long long nnz, int *d_rpt32)
+{
+    NSP_REQUIRE_CTX(ctx);
+    return nsp::rpt64_to_rpt32(ctx, M, d_rpt64, nnz, d_rpt32);
+}
+
+}  // extern "C"
+
+// ---- SpGEMM, host buffers ------------------------------------------------------------------
+template <typename real>
+static int upload_csr(nsp_context *ctx, int rows, const int *h_rpt, const int *h_col, const real *h_val,
+                      int *&d_rpt, int *&d_col, void *&d_val, int &row_cap, size_t &nnz_cap, int &nnz_out)
+{
+    const int nnz = h_rpt[rows];
+    nnz_out = nnz;
+    if (rows > row_cap || !d_rpt) {
+        cudaFree(d_rpt);
+        d_rpt = nullptr;
+        NSP_CUDA_TRY(ctx, cudaMalloc((void **)&d_rpt, sizeof(int) * ((size_t)rows + 1)));
+        row_cap = rows;
+    }
+    if ((size_t)nnz > nnz_cap || !d_col || ctx->host.in_val_bytes != (int)sizeof(real)) {
+        cudaFree(d_col);
+        cudaFree(d_val);
+        d_col = nullptr;
+        d_val = nullptr;
+        const size_t cap = (size_t)nnz + 1;
+        NSP_CUDA_TRY(ctx, cudaMalloc((void **)&d_col, sizeof(int) * cap));
+        NSP_CUDA_TRY(ctx, cudaMalloc((void **)&d_val, sizeof(real) * cap));
+        nnz_cap = cap;
+    }
+    cudaStream_t st = ctx->stream;
+    NSP_CUDA_TRY(ctx, cudaMemcpyAsync(d_rpt, h_rpt, sizeof(int) * ((size_t)rows + 1), cudaMemcpyHostToDevice, st));
+    NSP_CUDA_TRY(ctx, cudaMemcpyAsync(d_col, h_col, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    NSP_CUDA_TRY(ctx, cudaMemcpyAsync(d_val, h_val, sizeof(real) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+template <typename real>
+static int spgemm_host(nsp_context *ctx, int M, int K, int N, const int *h_a_rpt, const int *h_a_col,
+                       const real *h_a_val, const int *h_b_rpt, const int *h_b_col, const real *h_b_val,
+                       long long *h_nnz_c)
+{
+    if (M < 0 || K < 0 || N < 0 || !h_a_rpt || !h_b_rpt) return ctx->fail(NSP_ERR_ARG, "nsp_spgemm_host: bad argument");
+    nsp_host_result &h = ctx->host;
+    if (h.in_val_bytes != (int)sizeof(real)) {
+        // precision switch: drop the cached input buffers
+        cudaFree(h.d_a_col); cudaFree(h.d_a_val); cudaFree(h.d_b_col); cudaFree(h.d_b_val);
+        h.d_a_col = h.d_b_col = nullptr;
+        h.d_a_val = h.d_b_val = nullptr;
+        h.a_nnz_cap = h.b_nnz_cap = 0;
+    }
+    int a_nnz = 0, b_nnz = 0;
+    const bool same = (h_a_rpt == h_b_rpt && h_a_col == h_b_col && (const void *)h_a_val == (const void *)h_b_val && M == K);
+    if (upload_csr<real>(ctx, M, h_a_rpt, h_a_col, h_a_val, h.d_a_rpt, h.d_a_col, h.d_a_val, h.a_m_cap,
+                         h.a_nnz_cap, a_nnz) != 0)
+        return -1;
+    h.in_val_bytes = (int)sizeof(real);
+    const int *b_rpt = h.d_a_rpt, *b_col = h.d_a_col;
+    const real *b_val = (const real *)h.d_a_val;
+    if (!same) {
+        if (upload_csr<real>(ctx, K, h_b_rpt, h_b_col, h_b_val, h.d_b_rpt, h.d_b_col, h.d_b_val, h.b_m_cap,
+                             h.b_nnz_cap, b_nnz) != 0)
+            return -1;
+        b_rpt = h.d_b_rpt;
+        b_col = h.d_b_col;
+        b_val = (const real *)h.d_b_val;
+    }
+    if (h.M < M || !h.d_rpt64) {
+        cudaFree(h.d_rpt64);
+        h.d_rpt64 = nullptr;
+        NSP_CUDA_TRY(ctx, cudaMalloc((void **)&h.d_rpt64, sizeof(long long) * ((size_t)M + 1)));
+    }
+    h.M = M;
+    long long nnz = 0, ip = 0;
+    if (nsp::spgemm_symbolic(ctx, M, K, N, h.d_a_rpt, h.d_a_col, b_rpt, b_col, h.d_rpt64, &nnz, &ip) != 0)
+        return -1;
+    if (nnz > h.nnz || h.val_bytes != (int)sizeof(real) || !h.d_col) {
+        cudaFree(h.d_col);
+        cudaFree(h.d_val);
+        h.d_col = nullptr;
+        h.d_val = nullptr;
+        NSP_CUDA_TRY(ctx, cudaMalloc((void **)&h.d_col, sizeof(int) * (size_t)(nnz + 1)));
+        NSP_CUDA_TRY(ctx, cudaMalloc((void **)&h.d_val, sizeof(real) * (size_t)(nnz + 1)));
+    }
+    h.nnz = nnz;
+    h.val_bytes = (int)sizeof(real);
+    if (nsp::spgemm_numeric<real>(ctx, M, K, N, h.d_a_rpt, h.d_a_col, (const real *)h.d_a_val, b_rpt, b_col,
+                                  b_val, h.d_rpt64, h.d_col, (real *)h.d_val) != 0)
+        return -1;
+    if (h_nnz_c) *h_nnz_c = nnz;
+    return 0;
+}
+
+extern "C" {
+
+int nsp_spgemm_host_s(nsp_context *ctx, int M, int K, int N, const int *h_a_rpt, const int *h_a_col,
+                      const float *h_a_val, const int *h_b_rpt, const int *h_b_col, const float *h_b_val,
+                      long long *h_nnz_c)
+{
+    NSP_REQUIRE_CTX(ctx);
+    return spgemm_host<float>(ctx, M, K, N, h_a_rpt, h_a_col, h_a_val, h_b_rpt, h_b_col, h_b_val, h_nnz_c);
+}
+
+int nsp_spgemm_host_d(nsp_context *ctx, int M, int K, int N, const int *h_a_rpt, const int *h_a_col,
+                      const double *h_a_val, const int *h_b_rpt, const int *h_b_col, const double *h_b_val,
+                      long long *h_nnz_c)
+{
+    NSP_REQUIRE_CTX(ctx);
+    return spgemm_host<double>(ctx, M, K, N, h_a_rpt, h_a_col, h_a_val, h_b_rpt, h_b_col, h_b_val, h_nnz_c);
+}
+
+static int host_fetch(nsp_context *ctx, int val_bytes, long long *h_c_rpt64, int *h_c_col, void *h_c_val)
+{
+    nsp_host_result &h = ctx->host;
+    if (!h.d_rpt64 || h.val_bytes != val_bytes) return ctx->fail(NSP_ERR_ARG, "nsp_spgemm_host_fetch: no result of this precision on the context");
+    cudaStream_t st = ctx->stream;
+    if (h_c_rpt64)
+        NSP_CUDA_TRY(ctx, cudaMemcpyAsync(h_c_rpt64, h.d_rpt64, sizeof(long long) * ((size_t)h.M + 1), cudaMemcpyDeviceToHost, st));
+    if (h_c_col && h.nnz)
+        NSP_CUDA_TRY(ctx, cudaMemcpyAsync(h_c_col, h.d_col, sizeof(int) * (size_t)h.nnz, cudaMemcpyDeviceToHost, st));
+    if (h_c_val && h.nnz)
+        NSP_CUDA_TRY(ctx, cudaMemcpyAsync(h_c_val, h.d_val, (size_t)val_bytes * (size_t)h.nnz, cudaMemcpyDeviceToHost, st));
+    NSP_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+int nsp_spgemm_host_fetch_s(nsp_context *ctx, long long *h_c_rpt64, int *h_c_col, float *h_c_val)
+{
+    NSP_REQUIRE_CTX(ctx);
+    return host_fetch(ctx, 4, h_c_rpt64, h_c_col, h_c_val);
+}
+
+int nsp_spgemm_host_fetch_d(nsp_context *ctx, long long *h_c_rpt64, int *h_c_col, double *h_c_val)
+{
+    NSP_REQUIRE_CTX(ctx);
+    return host_fetch(ctx, 8, h_c_rpt64, h_c_col, h_c_val);
+}
+
+int nsp_spgemm_host_drain(nsp_context *ctx, void *h_stage, size_t stage_bytes, unsigned long long *h_checksum,
+                          long long *h_bytes)
+{
+    NSP_REQUIRE_CTX(ctx);
+    nsp_host_result &h = ctx->host;
+    if (!h.d_rpt64 || !h_stage || stage_bytes < 4096) return ctx->fail(NSP_ERR_ARG, "nsp_spgemm_host_drain: bad argument");
+    const size_t half = (stage_bytes / 2) & ~size_t(255);
+    cudaStream_t st = ctx->stream;
+    cudaEvent_t ev[2];
+    NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    unsigned long long sum = 0;
+    long long total = 0;
+    const void *src[3] = {h.d_rpt64, h.d_col, h.d_val};
+    const size_t len[3] = {sizeof(long long) * ((size_t)h.M + 1), sizeof(int) * (size_t)h.nnz,
+                           (size_t)h.val_bytes * (size_t)h.nnz};
+    int slot = 0;
+    bool pending[2] = {false, false};
+    size_t pend_len[2] = {0, 0};
+    auto consume = [&](int s) {
+        // fold the first and last word of the chunk: proves the bytes arrived without a host pass
+        // over tens of GB
+        cudaEventSynchronize(ev[s]);
+        const unsigned char *p = (const unsigned char *)h_stage + (size_t)s * half;
+        unsigned long long a = 0, b = 0;
+        memcpy(&a, p, pend_len[s] >= 8 ? 8 : pend_len[s]);
+        if (pend_len[s] >= 8) memcpy(&b, p + pend_len[s] - 8, 8);
+        sum = sum * 1099511628211ull + (a ^ (b << 1));
+        pending[s] = false;
+    };
+    for (int a = 0; a < 3; ++a) {
+        for (size_t off = 0; off < len[a]; off += half) {
+            const size_t n = len[a] - off < half ? len[a] - off : half;
+            if (pending[slot]) consume(slot);
+            NSP_CUDA_TRY(ctx, cudaMemcpyAsync((unsigned char *)h_stage + (size_t)slot * half,
+                                              (const unsigned char *)src[a] + off, n, cudaMemcpyDeviceToHost, st));
+            NSP_CUDA_TRY(ctx, cudaEventRecord(ev[slot], st));
+            pending[slot] = true;
+            pend_len[slot] = n;
+            total += (long long)n;
+            slot ^= 1;
+        }
+    }
+    if (pending[slot]) consume(slot);
+    if (pending[slot ^ 1]) consume(slot ^ 1);
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    if (h_checksum) *h_checksum = sum;
+    if (h_bytes) *h_bytes = total;
+    return 0;
+}
+
+int nsp_spgemm_host_release(nsp_context *ctx)
+{
+    NSP_REQUIRE_CTX(ctx);
+    nsp_host_result &h = ctx->host;
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(h.d_rpt64); cudaFree(h.d_col); cudaFree(h.d_val);
+    cudaFree(h.d_a_rpt); cudaFree(h.d_a_col); cudaFree(h.d_a_val);
+    cudaFree(h.d_b_rpt); cudaFree(h.d_b_col); cudaFree(h.d_b_val);
+    h = nsp_host_result();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// nsparse-b200: shared device/host helpers.  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace nsp {
+
+// ---------------------------------------------------------------------------------------------
+// hardware parameters of the B200 this library is written for.  The reference derives its bin
+// ladder from 48 KiB smem/block, 64 KiB/SM (spgemm_hash_kernel_gen.c:40-44); here the ladder is
+// derived from the 227 KiB opt-in limit and re-checked against cudaDeviceProp at context creation.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWarp = 32;
+constexpr int kMaxSmemOptin = 227 * 1024;   // bytes per CTA on sm_100
+constexpr int kEmptyKey = -1;               // columns are >= 0, so -1 marks a free slot (ref: init_check)
+constexpr unsigned kHashMul = 107u;         // HASH_SCAL of the reference (kernel_spgemm_hash_d.cu:30);
+                                            // applied to the UNSIGNED column so col >= 20,070,414 cannot
+                                            // overflow into negative hashes as it does in the reference
+
+struct Error {
+    int code;
+    std::string msg;
+};
+
+#define NSP_CUDA_TRY(ctx, expr)                                                                   \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            (ctx)->fail(-1, std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + \
+                                ":" + std::to_string(__LINE__));                                  \
+            return -1;                                                                            \
+        }                                                                                         \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_nc(const int *p) { return __ldg(p); }
+__device__ __forceinline__ float ld_nc(const float *p) { return __ldg(p); }
+__device__ __forceinline__ double ld_nc(const double *p) { return __ldg(p); }
+__device__ __forceinline__ long long ld_nc(const long long *p) { return __ldg(p); }
+
+// streamed (read-once) data: bypass L1 allocation so the gathered B rows keep the cache
+__device__ __forceinline__ int ld_stream(const int *p)
+{
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream(const float *p)
+{
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_stream(const double *p)
+{
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ unsigned hash_col(int col) { return (unsigned)col * kHashMul; }
+
+__host__ __device__ __forceinline__ int next_pow2_int(int v)
+{
+    // smallest power of two >= v, v >= 1
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// log2-style bin of a per-row count:  v <= (1<<s) -> 0 ; else ceil(log2(v)) - s
+__host__ __device__ __forceinline__ int log_bin(int v, int s)
+{
+    if (v <= (1 << s)) return 0;
+#ifdef __CUDA_ARCH__
+    return 32 - __clz(v - 1) - s;
+#else
+    int b = 0;
+    unsigned u = (unsigned)(v - 1);
+    while (u) {
+        ++b;
+        u >>= 1;
+    }
+    return b - s;
+#endif
+}
+
+constexpr int kNumBins = 28;   // log_bin(INT_MAX, 4) = 27
+
+}  // namespace nsp

@@ -1,0 +1,74 @@
+// nsparse-b200: context life cycle and the workspace arena.
+#include "context.h"
+
+int nsp_context::arena_reserve(size_t total_bytes)
+{
+    if (total_bytes <= arena_bytes) return 0;
+    // growing: nothing of ours may still be running on the old block
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return fail(-1, std::string("arena sync: ") + cudaGetErrorString(e));
+    if (arena) cudaFree(arena);
+    arena = nullptr;
+    arena_bytes = 0;
+    size_t want = total_bytes + total_bytes / 8 + (1u << 20);
+    e = cudaMalloc((void **)&arena, want);
+    if (e != cudaSuccess) return fail(-4, std::string("arena cudaMalloc: ") + cudaGetErrorString(e));
+    arena_bytes = want;
+    sp.symbolic_done = false;
+    return 0;
+}
+
+namespace nsp {
+
+int context_create(nsp_context **out, int device)
+{
+    if (!out) return -2;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        fprintf(stderr, "nsparse_b200: no CUDA device -- this library has no CPU fallback\n");
+        return -1;
+    }
+    if (device < 0 || device >= count) return -2;
+    if (cudaSetDevice(device) != cudaSuccess) return -1;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+    if (prop.major < 10) {
+        fprintf(stderr, "nsparse_b200: device %d is sm_%d%d; this build targets sm_100a (B200) only\n", device,
+                prop.major, prop.minor);
+        return -1;
+    }
+    nsp_context *ctx = new nsp_context();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    ctx->l2_bytes = (size_t)prop.l2CacheSize;
+    ctx->stream = nullptr;
+    *out = ctx;
+    return 0;
+}
+
+int context_destroy(nsp_context *ctx)
+{
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->sp.h_scalars) cudaFreeHost(ctx->sp.h_scalars);
+    if (ctx->sp.h_bins) cudaFreeHost(ctx->sp.h_bins);
+    if (ctx->sp.h_binsum) cudaFreeHost(ctx->sp.h_binsum);
+    nsp_host_result &h = ctx->host;
+    cudaFree(h.d_rpt64);
+    cudaFree(h.d_col);
+    cudaFree(h.d_val);
+    cudaFree(h.d_a_rpt);
+    cudaFree(h.d_a_col);
+    cudaFree(h.d_a_val);
+    cudaFree(h.d_b_rpt);
+    cudaFree(h.d_b_col);
+    cudaFree(h.d_b_val);
+    delete ctx;
+    return 0;
+}
+
+}  // namespace nsp

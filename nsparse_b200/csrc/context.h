@@ -1,0 +1,105 @@
+// nsparse-b200: the per-GPU context behind the C ABI (include/nsparse_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+// Everything a SpGEMM call needs between its symbolic and numeric phase.  Lives in the
+// context's arena; replaces sfBIN (nsparse.h:110-121), which the reference rebuilds per call.
+struct nsp_spgemm_state {
+    int M = 0, K = 0, N = 0;
+    int *d_row_cnt = nullptr;     // [M+1] nnz(C_i) after the symbolic phase
+    int *d_row_ip = nullptr;      // [M+1] min(intermediate products of row i, N)
+    int *d_row_perm = nullptr;    // [M]   rows grouped by bin, heaviest bin first
+    int *d_bins = nullptr;        // see spgemm_plan.h for the layout
+    unsigned long long *d_binsum = nullptr;
+    int *h_bins = nullptr;        // pinned mirrors
+    unsigned long long *h_binsum = nullptr;
+    long long *d_scalars = nullptr;   // [8]  total ip, nnz, ...
+    long long *d_scan_tmp = nullptr;  // block sums of the row-pointer scan
+    long long *h_scalars = nullptr;   // pinned mirror
+    int lanes_per_brow = 32;
+    bool symbolic_done = false;
+};
+
+struct nsp_host_result {
+    // C kept on the device by nsp_spgemm_host_*
+    long long *d_rpt64 = nullptr;
+    int *d_col = nullptr;
+    void *d_val = nullptr;
+    int M = 0;
+    long long nnz = 0;
+    int val_bytes = 0;
+    // device copies of the inputs
+    int *d_a_rpt = nullptr, *d_a_col = nullptr, *d_b_rpt = nullptr, *d_b_col = nullptr;
+    void *d_a_val = nullptr, *d_b_val = nullptr;
+    size_t a_nnz_cap = 0, b_nnz_cap = 0;
+    int a_m_cap = 0, b_m_cap = 0;
+    int in_val_bytes = 0;
+};
+
+struct nsp_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;   // nullptr = legacy default stream
+    int sm_count = 148;
+    int max_smem_optin = nsp::kMaxSmemOptin;
+    size_t l2_bytes = 0;
+
+    // grow-only arena for plan / workspace arrays
+    char *arena = nullptr;
+    size_t arena_bytes = 0;
+    size_t arena_used = 0;
+
+    // options (nsp_set_option)
+    long long opt_sym_bitmap_min = -1;   // rows with min(ip,N) >  this go to the bitmap kernel (-1: default)
+    long long opt_num_bitmap_min = -1;   // rows with nnz(C_i)  >  this go to the bitmap-rank kernel
+    long long opt_lanes_per_brow = 0;    // 0: pick from nnz(B)/K
+
+    nsp_spgemm_state sp;
+    nsp_host_result host;
+
+    long long launches = 0;
+    std::string err;
+
+    int fail(int code, const std::string &msg)
+    {
+        err = msg;
+        return code;
+    }
+
+    // Reserve `bytes` in the arena (256-byte aligned).  reset_arena() must have been called at
+    // the start of the operation; the arena is re-allocated (after a device sync) when too small.
+    int arena_reserve(size_t total_bytes);
+    void arena_reset() { arena_used = 0; }
+    template <typename T>
+    T *arena_take(size_t count)
+    {
+        size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+        if (arena_used + bytes > arena_bytes) return nullptr;
+        T *p = reinterpret_cast<T *>(arena + arena_used);
+        arena_used += bytes;
+        return p;
+    }
+};
+
+namespace nsp {
+
+int context_create(nsp_context **out, int device);
+int context_destroy(nsp_context *ctx);
+
+// ---- SpGEMM core (spgemm_plan.cu, spgemm_symbolic.cu, spgemm_numeric.cuh) -------------------
+int spgemm_flop(nsp_context *ctx, int M, const int *a_rpt, const int *a_col, const int *b_rpt,
+                long long *h_flop);
+int spgemm_symbolic(nsp_context *ctx, int M, int K, int N, const int *a_rpt, const int *a_col,
+                    const int *b_rpt, const int *b_col, long long *c_rpt64, long long *h_nnz,
+                    long long *h_ip);
+template <typename real>
+int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, const int *a_col,
+                   const real *a_val, const int *b_rpt, const int *b_col, const real *b_val,
+                   const long long *c_rpt64, int *c_col, real *c_val);
+int rpt64_to_rpt32(nsp_context *ctx, int M, const long long *rpt64, long long nnz, int *rpt32);
+
+}  // namespace nsp

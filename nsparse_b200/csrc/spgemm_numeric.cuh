@@ -1,0 +1,411 @@
+// nsparse-b200: NUMERIC phase of the hash SpGEMM -- column indices and values of C = A*B.
+//
+// Reference: set_min_bin + calculate_value_col_bin_* (kernel_spgemm_hash_d.cu:201-246, 631-1027,
+// 1187-1288).  Kept: rows re-binned by their exact nnz from the symbolic phase, per-row hash table
+// of (column, value) in shared memory, CAS on the key + floating-point atomic add on the value,
+// output rows sorted by ascending column, numerical zeros kept.  Re-designed for B200:
+//   * tables up to 16384 (key,value) slots (192 KiB in fp64; reference: 4096), sized per row and
+//     never above 3/4 load;
+//   * the whole table is sorted bitonically with the free slots (key 0xffffffff) sinking to the
+//     end, which replaces the global-atomic compaction (:904-912) AND the O(nnz^2) counting sort
+//     (:917-925) with O(n log^2 n) shared-memory work and no global atomics;
+//   * rows above the hash ladder (reference: each_gl with 2*max_nz global slots PER ROW and an
+//     O(nnz^2) sort in global memory, :929-1027) use a column-tile BITMAP + RANK scheme: pass 1
+//     marks the row's columns in a shared-memory bitmap, a CTA-wide scan turns it into ranks,
+//     C.col is emitted straight from the bitmap (already sorted), pass 2 adds every product into
+//     C.val[rpt + rank(col)] with red.global.add.  No table, no compaction, no sort, no workspace;
+//   * native fp64 atomics everywhere (reference SpMV/SpGEMM fall back to CAS loops on fp64).
+#pragma once
+
+#include "context.h"
+#include "spgemm_device.cuh"
+#include "spgemm_plan.h"
+
+namespace nsp {
+
+// ---- bin 0: nnz(C_i) <= 16; 4 threads per row, 32 slots (ref: calculate_value_col_bin_pwarp) ----
+constexpr int kPwNum = 4;
+constexpr int kPwNumSlots = 32;
+
+template <typename real>
+__global__ void __launch_bounds__(256)
+num_pwarp_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
+                 const real *__restrict__ a_val, const int *__restrict__ b_rpt,
+                 const int *__restrict__ b_col, const real *__restrict__ b_val,
+                 const long long *__restrict__ c_rpt, int *__restrict__ c_col, real *__restrict__ c_val,
+                 const int *__restrict__ row_perm, const int *__restrict__ bins)
+{
+    __shared__ int keys[(256 / kPwNum) * kPwNumSlots];
+    __shared__ real vals[(256 / kPwNum) * kPwNumSlots];
+    int lo, hi;
+    class_range(bins, 0, 0, lo, hi);
+    const int n = hi - lo;
+    const int lr = threadIdx.x / kPwNum, t = threadIdx.x % kPwNum;
+    int *mk = keys + lr * kPwNumSlots;
+    real *mv = vals + lr * kPwNumSlots;
+    for (int base = blockIdx.x * (256 / kPwNum); base < n; base += gridDim.x * (256 / kPwNum)) {
+        for (int i = t; i < kPwNumSlots; i += kPwNum) {
+            mk[i] = kEmptyKey;
+            mv[i] = real(0);
+        }
+        __syncwarp();
+        const int r = base + lr;
+        int rid = 0;
+        if (r < n) {
+            rid = row_perm[lo + r];
+            const int a_end = a_rpt[rid + 1];
+            for (int j = a_rpt[rid] + t; j < a_end; j += kPwNum) {
+                const int ac = ld_stream(a_col + j);
+                const real av = ld_stream(a_val + j);
+                const int ke = ld_nc(b_rpt + ac + 1);
+                for (int k = ld_nc(b_rpt + ac); k < ke; ++k)
+                    hash_accumulate(mk, mv, kPwNumSlots - 1, ld_nc(b_col + k), av * ld_nc(b_val + k));
+            }
+        }
+        __syncwarp();
+        if (r < n) {
+            // rank of every occupied slot among the row's keys = its position in the sorted row
+            const long long off = c_rpt[rid];
+            for (int i = t; i < kPwNumSlots; i += kPwNum) {
+                const int key = mk[i];
+                if (key == kEmptyKey) continue;
+                int rank = 0;
+#pragma unroll
+                for (int q = 0; q < kPwNumSlots; ++q) rank += (unsigned)mk[q] < (unsigned)key;
+                c_col[off + rank] = key;
+                c_val[off + rank] = mv[i];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- hash classes -------------------------------------------------------------------------------
+template <typename real, int GROUP, int BS, int LB>
+__global__ void __launch_bounds__(BS, (BS >= 1024 ? 1 : 2))
+num_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
+                const real *__restrict__ a_val, const int *__restrict__ b_rpt,
+                const int *__restrict__ b_col, const real *__restrict__ b_val,
+                const long long *__restrict__ c_rpt, int *__restrict__ c_col, real *__restrict__ c_val,
+                const int *__restrict__ row_perm, int *__restrict__ bins, int bin_lo, int bin_hi,
+                int queue, int tmax)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_row;
+    constexpr int NG = BS / GROUP;
+    constexpr int LBE = LB < GROUP ? LB : GROUP;
+    const int g = threadIdx.x / GROUP, t = threadIdx.x % GROUP;
+    // values first (8-byte aligned for fp64), then keys
+    real *vals = reinterpret_cast<real *>(smem_raw) + (size_t)g * tmax;
+    int *keys = reinterpret_cast<int *>(smem_raw + sizeof(real) * (size_t)NG * tmax) + (size_t)g * tmax;
+    int lo, hi;
+    class_range(bins, bin_lo, bin_hi, lo, hi);
+    const int n = hi - lo;
+    while (true) {
+        int r;
+        if (GROUP == 32) {
+            r = 0;
+            if (t == 0) r = atomicAdd(&bins[kBinQueue + queue], 1);
+            r = __shfl_sync(0xffffffffu, r, 0);
+        } else {
+            if (t == 0) s_row = atomicAdd(&bins[kBinQueue + queue], 1);
+            __syncthreads();
+            r = s_row;
+        }
+        if (r >= n) break;
+        const int rid = row_perm[lo + r];
+        const long long off = c_rpt[rid];
+        const int nnz = (int)(c_rpt[rid + 1] - off);
+        const int tsize = table_size_for(nnz, tmax);
+        const unsigned mask = (unsigned)tsize - 1u;
+        for (int i = t; i < tsize; i += GROUP) {
+            keys[i] = kEmptyKey;
+            vals[i] = real(0);
+        }
+        group_sync<GROUP>();
+        for_each_product<GROUP, LBE, true, real>(
+            t, a_rpt[rid], a_rpt[rid + 1], a_col, a_val, b_rpt, b_col, b_val,
+            [&](int c, real v) { hash_accumulate(keys, vals, mask, c, v); });
+        group_sync<GROUP>();
+        bitonic_sort_slots<GROUP, real>(keys, vals, tsize, t);
+        for (int i = t; i < nnz; i += GROUP) {
+            c_col[off + i] = keys[i];
+            c_val[off + i] = vals[i];
+        }
+        group_sync<GROUP>();
+    }
+}
+
+// ---- bitmap + rank class ------------------------------------------------------------------------
+// shared memory: bm[nw] 64-bit bitmap words of the column tile, pre[nw] exclusive popcount prefix
+template <typename real, int BS, int LB>
+__global__ void __launch_bounds__(BS, (BS >= 1024 ? 1 : 2))
+num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
+                  const real *__restrict__ a_val, const int *__restrict__ b_rpt,
+                  const int *__restrict__ b_col, const real *__restrict__ b_val,
+                  const long long *__restrict__ c_rpt, int *__restrict__ c_col, real *__restrict__ c_val,
+                  const int *__restrict__ row_perm, int *__restrict__ bins, int bin_lo, int bin_hi,
+                  int queue, int N, int tile_cols)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_row;
+    __shared__ int s_warp[BS / 32];
+    __shared__ int s_carry;
+    const int tile_words = tile_cols >> 6;
+    unsigned long long *bm = reinterpret_cast<unsigned long long *>(smem_raw);
+    unsigned *bm32 = reinterpret_cast<unsigned *>(smem_raw);
+    int *pre = reinterpret_cast<int *>(smem_raw + sizeof(unsigned long long) * (size_t)tile_words);
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    int lo, hi;
+    class_range(bins, bin_lo, bin_hi, lo, hi);
+    const int n = hi - lo;
+    while (true) {
+        if (t == 0) s_row = atomicAdd(&bins[kBinQueue + queue], 1);
+        __syncthreads();
+        const int r = s_row;
+        if (r >= n) break;
+        const int rid = row_perm[lo + r];
+        const int a_beg = a_rpt[rid], a_end = a_rpt[rid + 1];
+        long long out = c_rpt[rid];
+        for (int t0 = 0; t0 < N; t0 += tile_cols) {
+            const int ncols = min(tile_cols, N - t0);
+            const int nw = (ncols + 63) >> 6;
+            for (int i = t; i < nw; i += BS) bm[i] = 0ull;
+            if (t == 0) s_carry = 0;
+            __syncthreads();
+            // pass 1: structure of the tile
+            for_each_product<BS, LB, false, real>(
+                t, a_beg, a_end, a_col, a_val, b_rpt, b_col, b_val, [&](int c, real) {
+                    const unsigned cc = (unsigned)(c - t0);
+                    if (cc < (unsigned)ncols) {
+                        const unsigned bit = 1u << (cc & 31);
+                        if (!(*((volatile unsigned *)(bm32 + (cc >> 5))) & bit))
+                            atomicOr(bm32 + (cc >> 5), bit);
+                    }
+                });
+            __syncthreads();
+            // exclusive prefix of the per-word popcounts, BS words at a time
+            for (int base = 0; base < nw; base += BS) {
+                const int w = base + t;
+                const int carry = s_carry;   // written before the barrier that ended the last round
+                const int c = w < nw ? __popcll(bm[w]) : 0;
+                int inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                if (lane == 31) s_warp[wid] = inc;
+                __syncthreads();
+                if (wid == 0) {
+                    const int wv = lane < BS / 32 ? s_warp[lane] : 0;
+                    int winc = wv;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, winc, o);
+                        if (lane >= o) winc += v;
+                    }
+                    if (lane < BS / 32) s_warp[lane] = winc - wv;
+                    if (lane == 31) s_carry = carry + winc;
+                }
+                __syncthreads();
+                if (w < nw) pre[w] = carry + s_warp[wid] + inc - c;
+                __syncthreads();
+            }
+            const int tile_nnz = s_carry;
+            // emit the (sorted) columns of the tile and clear their values
+            for (int w = t; w < nw; w += BS) {
+                unsigned long long bits = bm[w];
+                long long p = out + pre[w];
+                const int cbase = t0 + (w << 6);
+                while (bits) {
+                    const int b = __ffsll((long long)bits) - 1;
+                    bits &= bits - 1;
+                    c_col[p] = cbase + b;
+                    c_val[p] = real(0);
+                    ++p;
+                }
+            }
+            __syncthreads();
+            // pass 2: values
+            for_each_product<BS, LB, true, real>(
+                t, a_beg, a_end, a_col, a_val, b_rpt, b_col, b_val, [&](int c, real v) {
+                    const unsigned cc = (unsigned)(c - t0);
+                    if (cc < (unsigned)ncols) {
+                        const unsigned w = cc >> 6;
+                        const int rank =
+                            pre[w] + __popcll(bm[w] & ((1ull << (cc & 63)) - 1ull));
+                        atomicAdd(c_val + out + rank, v);
+                    }
+                });
+            out += tile_nnz;
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static inline int num_lanes_for(const nsp_context *ctx, const nsp_spgemm_state &sp, int bin_lo, int bin_hi)
+{
+    if (ctx->opt_lanes_per_brow > 0) return (int)ctx->opt_lanes_per_brow;
+    unsigned long long ip = 0, len = 0;
+    for (int b = bin_lo; b <= bin_hi; ++b) {
+        ip += sp.h_binsum[kSumIp + b];
+        len += sp.h_binsum[kSumLen + b];
+    }
+    const double avg = len ? (double)ip / (double)len : 0.0;
+    if (avg >= 24.0) return 32;
+    if (avg >= 12.0) return 16;
+    if (avg >= 6.0) return 8;
+    return 4;
+}
+
+static inline long long num_rows_in(const nsp_spgemm_state &sp, int bin_lo, int bin_hi)
+{
+    long long n = 0;
+    for (int b = bin_lo; b <= bin_hi; ++b) n += sp.h_bins[kBinHist + b];
+    return n;
+}
+
+static inline int num_imin(long long a, long long b) { return (int)(a < b ? a : b); }
+
+#define NSP_NUM_ARGS                                                                               \
+    a_rpt, a_col, a_val, b_rpt, b_col, b_val, c_rpt64, c_col, c_val, sp.d_row_perm, sp.d_bins
+
+template <typename real, int GROUP, int BS>
+static int launch_num_hash(nsp_context *ctx, int lanes, int grid, size_t smem, const int *a_rpt,
+                           const int *a_col, const real *a_val, const int *b_rpt, const int *b_col,
+                           const real *b_val, const long long *c_rpt64, int *c_col, real *c_val,
+                           int bin_lo, int bin_hi, int queue, int tmax)
+{
+    nsp_spgemm_state &sp = ctx->sp;
+#define NSP_NUM_LAUNCH(LBV)                                                                        \
+    {                                                                                              \
+        auto kern = num_hash_kernel<real, GROUP, BS, LBV>;                                         \
+        NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                               (int)smem));                                        \
+        kern<<<grid, BS, smem, ctx->stream>>>(NSP_NUM_ARGS, bin_lo, bin_hi, queue, tmax);          \
+    }
+    switch (lanes) {
+        case 4: NSP_NUM_LAUNCH(4) break;
+        case 8: NSP_NUM_LAUNCH(8) break;
+        case 16: NSP_NUM_LAUNCH(16) break;
+        default: NSP_NUM_LAUNCH(32) break;
+    }
+#undef NSP_NUM_LAUNCH
+    ctx->launches += 1;
+    NSP_CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+template <typename real>
+static int launch_num_bitmap(nsp_context *ctx, int lanes, int grid, size_t smem, const int *a_rpt,
+                             const int *a_col, const real *a_val, const int *b_rpt, const int *b_col,
+                             const real *b_val, const long long *c_rpt64, int *c_col, real *c_val,
+                             int bin_lo, int bin_hi, int queue, int N, int tile_cols)
+{
+    nsp_spgemm_state &sp = ctx->sp;
+#define NSP_NUM_LAUNCH(LBV)                                                                        \
+    {                                                                                              \
+        auto kern = num_bitmap_kernel<real, 1024, LBV>;                                            \
+        NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                               (int)smem));                                        \
+        kern<<<grid, 1024, smem, ctx->stream>>>(NSP_NUM_ARGS, bin_lo, bin_hi, queue, N, tile_cols); \
+    }
+    switch (lanes) {
+        case 4: NSP_NUM_LAUNCH(4) break;
+        case 8: NSP_NUM_LAUNCH(8) break;
+        case 16: NSP_NUM_LAUNCH(16) break;
+        default: NSP_NUM_LAUNCH(32) break;
+    }
+#undef NSP_NUM_LAUNCH
+    ctx->launches += 1;
+    NSP_CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+template <typename real>
+int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, const int *a_col,
+                   const real *a_val, const int *b_rpt, const int *b_col, const real *b_val,
+                   const long long *c_rpt64, int *c_col, real *c_val)
+{
+    nsp_spgemm_state &sp = ctx->sp;
+    if (!sp.symbolic_done || sp.M != M || sp.K != K || sp.N != N)
+        return ctx->fail(-2, "nsp_spgemm_numeric: call nsp_spgemm_symbolic on the same context and shapes first");
+    if (M == 0) return 0;
+    if (plan_by_count(ctx, M, kNumShift, a_rpt) != 0) return -1;
+
+    // ---- class ladder (numeric shift 4: bin b holds 2^(3+b) < nnz <= 2^(4+b)) ----
+    //   bin 0          <= 16        4 threads / row, 32 slots
+    //   bins 1..4      <= 256       warp / row, <= 512 slots, 8 rows per CTA
+    //   bins 5..7      <= 2048      CTA(256) / row, <= 4096 slots
+    //   bins 8..9      <= 8192      CTA(1024) / row, <= 16384 slots (128 KiB fp32 / 192 KiB fp64)
+    //   bins >= bm_bin              CTA(1024) / row, bitmap + rank over column tiles
+    const int smem_cap = ctx->max_smem_optin - 2048;
+    const int tile_max = (smem_cap / 12) * 64;
+    const int tile_cols = N < tile_max ? ((N + 63) / 64) * 64 : tile_max;
+    const int slot_bytes = 4 + (int)sizeof(real);
+    int bm_bin = 10;
+    if (N <= tile_max) {
+        const int v = (int)((long long)N * 9 / (64ll * slot_bytes)) + 1;
+        bm_bin = log_bin(v, kNumShift);
+        if (bm_bin < 5) bm_bin = 5;
+        if (bm_bin > 10) bm_bin = 10;
+    }
+    if (ctx->opt_num_bitmap_min >= 0) {
+        bm_bin = log_bin(num_imin(ctx->opt_num_bitmap_min, 0x7fffffff), kNumShift) + 1;
+        if (bm_bin < 1) bm_bin = 1;
+        if (bm_bin > 10) bm_bin = 10;
+    }
+    const int sms = ctx->sm_count;
+    if (num_rows_in(sp, bm_bin, kNumBins - 1) > 0) {
+        const size_t smem = (size_t)(tile_cols / 64) * 12;
+        const int per_sm = (smem + 2048) * 2 <= (size_t)ctx->max_smem_optin ? 2 : 1;
+        const int grid = num_imin(num_rows_in(sp, bm_bin, kNumBins - 1), (long long)sms * per_sm);
+        if (launch_num_bitmap<real>(ctx, num_lanes_for(ctx, sp, bm_bin, kNumBins - 1), grid, smem, a_rpt,
+                                    a_col, a_val, b_rpt, b_col, b_val, c_rpt64, c_col, c_val, bm_bin,
+                                    kNumBins - 1, 4, N, tile_cols) != 0)
+            return -1;
+    }
+    if (bm_bin > 8 && num_rows_in(sp, 8, num_imin(9, bm_bin - 1)) > 0) {
+        const int hi = num_imin(9, bm_bin - 1);
+        const int tmax = 16384;
+        const int grid = num_imin(num_rows_in(sp, 8, hi), sms);
+        if (launch_num_hash<real, 1024, 1024>(ctx, num_lanes_for(ctx, sp, 8, hi), grid,
+                                              (size_t)tmax * slot_bytes, a_rpt, a_col, a_val, b_rpt, b_col,
+                                              b_val, c_rpt64, c_col, c_val, 8, hi, 3, tmax) != 0)
+            return -1;
+    }
+    if (bm_bin > 5 && num_rows_in(sp, 5, num_imin(7, bm_bin - 1)) > 0) {
+        const int hi = num_imin(7, bm_bin - 1);
+        const int tmax = 4096;
+        const int grid = num_imin(num_rows_in(sp, 5, hi), (long long)sms * 4);
+        if (launch_num_hash<real, 256, 256>(ctx, num_lanes_for(ctx, sp, 5, hi), grid,
+                                            (size_t)tmax * slot_bytes, a_rpt, a_col, a_val, b_rpt, b_col,
+                                            b_val, c_rpt64, c_col, c_val, 5, hi, 2, tmax) != 0)
+            return -1;
+    }
+    if (num_rows_in(sp, 1, num_imin(4, bm_bin - 1)) > 0) {
+        const int hi = num_imin(4, bm_bin - 1);
+        const int tmax = 512;
+        const int grid = num_imin((num_rows_in(sp, 1, hi) + 7) / 8, (long long)sms * 4);
+        if (launch_num_hash<real, 32, 256>(ctx, num_lanes_for(ctx, sp, 1, hi), grid,
+                                           (size_t)tmax * slot_bytes * 8, a_rpt, a_col, a_val, b_rpt, b_col,
+                                           b_val, c_rpt64, c_col, c_val, 1, hi, 1, tmax) != 0)
+            return -1;
+    }
+    if (num_rows_in(sp, 0, 0) > 0) {
+        const int grid = num_imin((num_rows_in(sp, 0, 0) + 63) / 64, (long long)sms * 8);
+        num_pwarp_kernel<real><<<grid, 256, 0, ctx->stream>>>(a_rpt, a_col, a_val, b_rpt, b_col, b_val,
+                                                              c_rpt64, c_col, c_val, sp.d_row_perm, sp.d_bins);
+        ctx->launches += 1;
+        NSP_CUDA_TRY(ctx, cudaGetLastError());
+    }
+    return 0;
+}
+
+#undef NSP_NUM_ARGS
+
+}  // namespace nsp

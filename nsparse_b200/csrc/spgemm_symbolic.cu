@@ -1,0 +1,334 @@
+// nsparse-b200: SYMBOLIC phase of the hash SpGEMM -- exact nnz of every row of C = A*B.
+//
+// Reference: set_row_nnz + set_row_nz_bin_* (kernel_spgemm_hash_d.cu:266-622, 1077-1185).
+// What is kept: row-wise Gustavson, rows binned by an upper bound of their size, one hash set
+// per row probed linearly with hash = (col * 107) & (size - 1), table in shared memory.
+// What is re-designed for B200:
+//   * ladder derived from 227 KiB of shared memory: hash sets up to 32768 keys (reference: 8192);
+//     every table is sized per ROW (next pow2 of 4/3 * bound), so clearing it costs what the row
+//     needs, not what the bin allows, and the load factor never exceeds 3/4 (reference: up to 1).
+//   * rows above the hash ladder use a shared-memory BITMAP over a column tile instead of the
+//     try-then-redo pair each_tb_large / each_gl (:474-622) whose global table needs
+//     fail_count * max_intprod ints.  Bits are tested before the atomicOr, so the atomic count is
+//     nnz(C_i), not the number of products.  Columns beyond one tile (N > ~1.8 M) take one pass
+//     per tile; memory use is fixed and there is no failure path.
+//   * persistent CTAs pull rows from a queue ordered heaviest-first (no tail from 9.7 M-product
+//     rows landing last); no warp-synchronous assumptions: every phase boundary is a barrier.
+#include "context.h"
+#include "spgemm_device.cuh"
+#include "spgemm_plan.h"
+
+namespace nsp {
+
+// ---- bin 0: at most 32 products; 4 threads per row, 64-slot table (ref: set_row_nz_bin_pwarp) ----
+constexpr int kPw = 4;
+constexpr int kPwSymSlots = 64;
+
+__global__ void __launch_bounds__(256)
+sym_pwarp_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
+                 const int *__restrict__ b_rpt, const int *__restrict__ b_col,
+                 const int *__restrict__ row_perm, int *__restrict__ row_cnt,
+                 const int *__restrict__ bins)
+{
+    __shared__ int tab[(256 / kPw) * kPwSymSlots];
+    int lo, hi;
+    class_range(bins, 0, 0, lo, hi);
+    const int n = hi - lo;
+    const int lr = threadIdx.x / kPw, t = threadIdx.x % kPw;
+    int *my = tab + lr * kPwSymSlots;
+    for (int base = blockIdx.x * (256 / kPw); base < n; base += gridDim.x * (256 / kPw)) {
+        for (int i = t; i < kPwSymSlots; i += kPw) my[i] = kEmptyKey;
+        __syncwarp();
+        const int r = base + lr;
+        int cnt = 0, rid = 0;
+        if (r < n) {
+            rid = row_perm[lo + r];
+            const int a_end = a_rpt[rid + 1];
+            for (int j = a_rpt[rid] + t; j < a_end; j += kPw) {
+                const int ac = ld_stream(a_col + j);
+                const int ke = ld_nc(b_rpt + ac + 1);
+                for (int k = ld_nc(b_rpt + ac); k < ke; ++k)
+                    cnt += hash_insert_key(my, kPwSymSlots - 1, ld_nc(b_col + k));
+            }
+        }
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+        if (r < n && t == 0) row_cnt[rid] = cnt;
+        __syncwarp();
+    }
+}
+
+// ---- hash classes: a group (warp or CTA) per row, table of `tmax` keys per group -----------------
+template <int GROUP, int BS, int LB>
+__global__ void __launch_bounds__(BS, (BS >= 1024 ? 1 : 2))
+sym_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
+                const int *__restrict__ b_rpt, const int *__restrict__ b_col,
+                const int *__restrict__ row_perm, const int *__restrict__ row_ip,
+                int *__restrict__ row_cnt, int *__restrict__ bins, int bin_lo, int bin_hi, int queue,
+                int tmax)
+{
+    extern __shared__ int smem_i[];
+    __shared__ int s_row, s_cnt;
+    constexpr int LBE = LB < GROUP ? LB : GROUP;
+    const int g = threadIdx.x / GROUP, t = threadIdx.x % GROUP;
+    int *tab = smem_i + g * tmax;
+    int lo, hi;
+    class_range(bins, bin_lo, bin_hi, lo, hi);
+    const int n = hi - lo;
+    while (true) {
+        int r;
+        if (GROUP == 32) {
+            r = 0;
+            if (t == 0) r = atomicAdd(&bins[kBinQueue + queue], 1);
+            r = __shfl_sync(0xffffffffu, r, 0);
+        } else {
+            if (t == 0) {
+                s_row = atomicAdd(&bins[kBinQueue + queue], 1);
+                s_cnt = 0;
+            }
+            __syncthreads();
+            r = s_row;
+        }
+        if (r >= n) break;
+        const int rid = row_perm[lo + r];
+        const int tsize = table_size_for(row_ip[rid], tmax);
+        const unsigned mask = (unsigned)tsize - 1u;
+        for (int i = t; i < tsize; i += GROUP) tab[i] = kEmptyKey;
+        group_sync<GROUP>();
+        int cnt = 0;
+        for_each_product<GROUP, LBE, false, float>(
+            t, a_rpt[rid], a_rpt[rid + 1], a_col, (const float *)nullptr, b_rpt, b_col,
+            (const float *)nullptr, [&](int c, float) { cnt += hash_insert_key(tab, mask, c); });
+        cnt = warp_sum(cnt);
+        if (GROUP == 32) {
+            if (t == 0) row_cnt[rid] = cnt;
+            __syncwarp();
+        } else {
+            if ((t & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+            __syncthreads();
+            if (t == 0) row_cnt[rid] = s_cnt;
+            __syncthreads();
+        }
+    }
+}
+
+// ---- bitmap class: one CTA per row, one pass over the row's products per column tile -------------
+template <int BS, int LB>
+__global__ void __launch_bounds__(BS, (BS >= 1024 ? 1 : 2))
+sym_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
+                  const int *__restrict__ b_rpt, const int *__restrict__ b_col,
+                  const int *__restrict__ row_perm, int *__restrict__ row_cnt, int *__restrict__ bins,
+                  int bin_lo, int bin_hi, int queue, int N, int tile_cols)
+{
+    extern __shared__ int smem_i[];
+    unsigned *bm = reinterpret_cast<unsigned *>(smem_i);
+    __shared__ int s_row, s_cnt;
+    const int t = threadIdx.x;
+    int lo, hi;
+    class_range(bins, bin_lo, bin_hi, lo, hi);
+    const int n = hi - lo;
+    while (true) {
+        if (t == 0) {
+            s_row = atomicAdd(&bins[kBinQueue + queue], 1);
+            s_cnt = 0;
+        }
+        __syncthreads();
+        const int r = s_row;
+        if (r >= n) break;
+        const int rid = row_perm[lo + r];
+        const int a_beg = a_rpt[rid], a_end = a_rpt[rid + 1];
+        for (int t0 = 0; t0 < N; t0 += tile_cols) {
+            const int ncols = min(tile_cols, N - t0);
+            const int nw = (ncols + 31) >> 5;
+            for (int i = t; i < nw; i += BS) bm[i] = 0u;
+            __syncthreads();
+            for_each_product<BS, LB, false, float>(
+                t, a_beg, a_end, a_col, (const float *)nullptr, b_rpt, b_col, (const float *)nullptr,
+                [&](int c, float) {
+                    const unsigned cc = (unsigned)(c - t0);
+                    if (cc < (unsigned)ncols) {
+                        const unsigned bit = 1u << (cc & 31);
+                        if (!(*((volatile unsigned *)(bm + (cc >> 5))) & bit)) atomicOr(bm + (cc >> 5), bit);
+                    }
+                });
+            __syncthreads();
+            int cnt = 0;
+            for (int i = t; i < nw; i += BS) cnt += __popc(bm[i]);
+            cnt = warp_sum(cnt);
+            if ((t & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+            __syncthreads();
+        }
+        if (t == 0) row_cnt[rid] = s_cnt;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int lanes_for(const nsp_context *ctx, const nsp_spgemm_state &sp, int bin_lo, int bin_hi)
+{
+    if (ctx->opt_lanes_per_brow > 0) return (int)ctx->opt_lanes_per_brow;
+    unsigned long long ip = 0, len = 0;
+    for (int b = bin_lo; b <= bin_hi; ++b) {
+        ip += sp.h_binsum[kSumIp + b];
+        len += sp.h_binsum[kSumLen + b];
+    }
+    const double avg = len ? (double)ip / (double)len : 0.0;
+    if (avg >= 24.0) return 32;
+    if (avg >= 12.0) return 16;
+    if (avg >= 6.0) return 8;
+    return 4;
+}
+
+static long long rows_in(const nsp_spgemm_state &sp, int bin_lo, int bin_hi)
+{
+    long long n = 0;
+    for (int b = bin_lo; b <= bin_hi; ++b) n += sp.h_bins[kBinHist + b];
+    return n;
+}
+
+template <int GROUP, int BS>
+static int launch_sym_hash(nsp_context *ctx, int lanes, int grid, size_t smem, const int *a_rpt,
+                           const int *a_col, const int *b_rpt, const int *b_col, int bin_lo, int bin_hi,
+                           int queue, int tmax)
+{
+    nsp_spgemm_state &sp = ctx->sp;
+#define NSP_SYM_LAUNCH(LBV)                                                                         \
+    {                                                                                               \
+        auto kern = sym_hash_kernel<GROUP, BS, LBV>;                                                \
+        NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                               (int)smem));                                         \
+        kern<<<grid, BS, smem, ctx->stream>>>(a_rpt, a_col, b_rpt, b_col, sp.d_row_perm, sp.d_row_ip, \
+                                              sp.d_row_cnt, sp.d_bins, bin_lo, bin_hi, queue, tmax); \
+    }
+    switch (lanes) {
+        case 4: NSP_SYM_LAUNCH(4) break;
+        case 8: NSP_SYM_LAUNCH(8) break;
+        case 16: NSP_SYM_LAUNCH(16) break;
+        default: NSP_SYM_LAUNCH(32) break;
+    }
+#undef NSP_SYM_LAUNCH
+    ctx->launches += 1;
+    NSP_CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+static int launch_sym_bitmap(nsp_context *ctx, int lanes, int grid, size_t smem, const int *a_rpt,
+                             const int *a_col, const int *b_rpt, const int *b_col, int bin_lo,
+                             int bin_hi, int queue, int N, int tile_cols)
+{
+    nsp_spgemm_state &sp = ctx->sp;
+#define NSP_SYM_LAUNCH(LBV)                                                                         \
+    {                                                                                               \
+        auto kern = sym_bitmap_kernel<1024, LBV>;                                                   \
+        NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                               (int)smem));                                         \
+        kern<<<grid, 1024, smem, ctx->stream>>>(a_rpt, a_col, b_rpt, b_col, sp.d_row_perm,          \
+                                                sp.d_row_cnt, sp.d_bins, bin_lo, bin_hi, queue, N,  \
+                                                tile_cols);                                         \
+    }
+    switch (lanes) {
+        case 4: NSP_SYM_LAUNCH(4) break;
+        case 8: NSP_SYM_LAUNCH(8) break;
+        case 16: NSP_SYM_LAUNCH(16) break;
+        default: NSP_SYM_LAUNCH(32) break;
+    }
+#undef NSP_SYM_LAUNCH
+    ctx->launches += 1;
+    NSP_CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+static inline int imin(long long a, long long b) { return (int)(a < b ? a : b); }
+
+int spgemm_symbolic(nsp_context *ctx, int M, int K, int N, const int *a_rpt, const int *a_col,
+                    const int *b_rpt, const int *b_col, long long *c_rpt64, long long *h_nnz,
+                    long long *h_ip)
+{
+    if (M < 0 || K < 0 || N < 0 || !c_rpt64) return ctx->fail(-2, "nsp_spgemm_symbolic: bad argument");
+    nsp_spgemm_state &sp = ctx->sp;
+    sp.symbolic_done = false;
+    sp.M = M;
+    sp.K = K;
+    sp.N = N;
+    if (plan_reserve(ctx, M) != 0) return -1;
+    if (plan_by_intprod(ctx, M, N > 0 ? N : 1, a_rpt, a_col, b_rpt) != 0) return -1;
+
+    // ---- class ladder (symbolic shift 5: bin b holds 2^(4+b) < v <= 2^(5+b)) ----
+    //   bin 0          <= 32        4 threads / row, 64 slots
+    //   bins 1..4      <= 512       warp / row, <= 1024 slots, 8 rows per CTA
+    //   bins 5..7      <= 4096      CTA(256) / row, <= 8192 slots (32 KiB)
+    //   bins 8..9      <= 16384     CTA(1024) / row, <= 32768 slots (128 KiB)
+    //   bins >= bm_bin              CTA(1024) / row, bitmap over column tiles
+    const int smem_cap = ctx->max_smem_optin - 1024;
+    const int tile_max = (smem_cap / 4) * 32;                      // columns one bitmap tile can hold
+    const int tile_cols = N < tile_max ? ((N + 31) / 32) * 32 : tile_max;
+    int bm_bin = 10;
+    if (N <= tile_max) {
+        // one tile covers the row: switch to the bitmap as soon as it is no bigger than the hash set
+        const int v = N / 43 + 1;
+        bm_bin = log_bin(v, kSymShift);
+        if (bm_bin < 5) bm_bin = 5;
+        if (bm_bin > 10) bm_bin = 10;
+    }
+    if (ctx->opt_sym_bitmap_min >= 0) {
+        bm_bin = log_bin(imin(ctx->opt_sym_bitmap_min, 0x7fffffff), kSymShift) + 1;
+        if (bm_bin < 1) bm_bin = 1;
+        if (bm_bin > 10) bm_bin = 10;
+    }
+    const int sms = ctx->sm_count;
+    if (M > 0) {
+        // heaviest first
+        if (rows_in(sp, bm_bin, kNumBins - 1) > 0) {
+            const int lanes = lanes_for(ctx, sp, bm_bin, kNumBins - 1);
+            const size_t smem = (size_t)(tile_cols / 32) * 4;
+            const int per_sm = smem > 0 ? imin((size_t)smem_cap / (smem + 1024) , 2) : 2;
+            const int grid = imin(rows_in(sp, bm_bin, kNumBins - 1), (long long)sms * (per_sm < 1 ? 1 : per_sm));
+            if (launch_sym_bitmap(ctx, lanes, grid, smem, a_rpt, a_col, b_rpt, b_col, bm_bin, kNumBins - 1, 4,
+                                  N, tile_cols) != 0)
+                return -1;
+        }
+        if (bm_bin > 8 && rows_in(sp, 8, imin(9, bm_bin - 1)) > 0) {
+            const int hi = imin(9, bm_bin - 1);
+            const int tmax = 32768;
+            const int grid = imin(rows_in(sp, 8, hi), sms);
+            if (launch_sym_hash<1024, 1024>(ctx, lanes_for(ctx, sp, 8, hi), grid, (size_t)tmax * 4, a_rpt, a_col,
+                                            b_rpt, b_col, 8, hi, 3, tmax) != 0)
+                return -1;
+        }
+        if (bm_bin > 5 && rows_in(sp, 5, imin(7, bm_bin - 1)) > 0) {
+            const int hi = imin(7, bm_bin - 1);
+            const int tmax = 8192;
+            const int grid = imin(rows_in(sp, 5, hi), (long long)sms * 6);
+            if (launch_sym_hash<256, 256>(ctx, lanes_for(ctx, sp, 5, hi), grid, (size_t)tmax * 4, a_rpt, a_col,
+                                          b_rpt, b_col, 5, hi, 2, tmax) != 0)
+                return -1;
+        }
+        if (rows_in(sp, 1, imin(4, bm_bin - 1)) > 0) {
+            const int hi = imin(4, bm_bin - 1);
+            const int tmax = 1024;
+            const int grid = imin((rows_in(sp, 1, hi) + 7) / 8, (long long)sms * 6);
+            if (launch_sym_hash<32, 256>(ctx, lanes_for(ctx, sp, 1, hi), grid, (size_t)tmax * 4 * 8, a_rpt, a_col,
+                                         b_rpt, b_col, 1, hi, 1, tmax) != 0)
+                return -1;
+        }
+        if (rows_in(sp, 0, 0) > 0) {
+            const int grid = imin((rows_in(sp, 0, 0) + 63) / 64, (long long)sms * 8);
+            sym_pwarp_kernel<<<grid, 256, 0, ctx->stream>>>(a_rpt, a_col, b_rpt, b_col, sp.d_row_perm,
+                                                          sp.d_row_cnt, sp.d_bins);
+            ctx->launches += 1;
+            NSP_CUDA_TRY(ctx, cudaGetLastError());
+        }
+    }
+    if (scan_row_counts(ctx, M, c_rpt64) != 0) return -1;
+    NSP_CUDA_TRY(ctx, cudaMemcpyAsync(sp.h_scalars, sp.d_scalars, sizeof(long long) * 8,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    NSP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_nnz) *h_nnz = sp.h_scalars[kScalarNnz];
+    if (h_ip) *h_ip = sp.h_scalars[kScalarIp];
+    sp.symbolic_done = true;
+    return 0;
+}
+
+}  // namespace nsp
