@@ -150,15 +150,12 @@ def powerlaw_csr(n: int, mean_nnz: int = 64, max_row: int = 65536, seed: int = 7
     # sorted distinct columns per row: stratified sampling (one column per equal-width stratum)
     row_of = np.repeat(np.arange(n, dtype=np.int64), lens)
     k = np.arange(total, dtype=np.int64) - rpt[row_of]
-    width = n / lens[row_of].astype(np.float64)
-    u = rng.random(total)
-    cols = np.minimum((k + u) * width, n - 1).astype(np.int64)
-    # strata narrower than 1 column cannot happen (lens <= n); equal neighbours only when width < 2
-    same = np.flatnonzero((cols[1:] <= cols[:-1]) & (row_of[1:] == row_of[:-1])) + 1
-    while len(same):
-        cols[same] = cols[same - 1] + 1
-        same = same[(cols[same] <= cols[same - 1])]
-    cols = np.minimum(cols, n - 1)
+    # integer strata [k*n/len, (k+1)*n/len): non-empty because len <= n, disjoint and ordered, so
+    # one draw per stratum gives strictly increasing columns
+    ln = lens[row_of]
+    base = (k * n) // ln
+    size = ((k + 1) * n) // ln - base
+    cols = base + np.minimum((rng.random(total) * size).astype(np.int64), size - 1)
     if values == "uniform":
         val = _uniform_values(total, seed, dtype)
     else:

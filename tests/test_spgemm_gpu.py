@@ -1,0 +1,251 @@
+"""GPU parity tests of the hash SpGEMM against the CPU oracle, through the C ABI.
+
+Bar (BASELINE.json north_star): nnz, row pointer and column indices bit-exact; values within
+1e-6 relative (fp32) / 1e-12 (fp64).  Integer-valued inputs make every sum exact, so for those the
+values are required to be BIT-exact as well (any summation order gives the same float).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "test_mtx.json")))
+
+
+@pytest.fixture(scope="module")
+def ns():
+    import nsparse_b200 as ns
+
+    ns.load_library()
+    return ns
+
+
+@pytest.fixture(scope="module")
+def ctx(ns):
+    return ns.Context(0)
+
+
+def _run(ns, ctx, a, b):
+    a.memcpy()
+    b.memcpy()
+    c = ns.spgemm_kernel_hash(a, b, ctx)
+    ctx.sync()
+    return c, c.to_host()
+
+
+def _oracle(a, b):
+    return oracle.spgemm(a.rpt, a.col, a.val, b.rpt, b.col, b.val, acc_double=True)
+
+
+def _check(ns, ctx, a, b, exact_values=False):
+    c, got = _run(ns, ctx, a, b)
+    want = _oracle(a, b)
+    assert c.nnz == int(want[0][-1])
+    assert c.intprod * 2 == oracle.spgemm_flop(a.rpt, a.col, b.rpt)
+    ok, msg = oracle.check_spgemm_answer(got, want)
+    assert ok, msg
+    if exact_values:
+        assert np.array_equal(got[2], want[2])
+    return c, got
+
+
+def _rand(ns, m, n, density, seed, dtype, ints=True, sort=True):
+    rng = np.random.default_rng(seed)
+    a = sp.random(m, n, density=density, random_state=rng, format="csr", dtype=np.float64)
+    a.data = rng.integers(1, 4, size=a.nnz).astype(dtype) if ints else rng.random(a.nnz).astype(dtype)
+    a.sort_indices()
+    return ns.CSR.from_scipy(a, dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_golden_test_mtx(ns, ctx, dtype):
+    """Config C1: data/test.mtx, C = A^2, against the committed golden vectors."""
+    a = ns.CSR(GOLD["M"], GOLD["N"], GOLD["rpt"], GOLD["col"], np.array(GOLD["val"], dtype))
+    a.memcpy()
+    assert ns.get_spgemm_flop(a, a, ctx) == GOLD["flop"]
+    c, (rpt, col, val) = _run(ns, ctx, a, a)
+    assert c.nnz == GOLD["c_nnz"] and c.intprod * 2 == GOLD["flop"]
+    assert rpt.tolist() == GOLD["c_rpt"] and col.tolist() == GOLD["c_col"] and val.tolist() == GOLD["c_val"]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("m,k,n,dens", [(1, 1, 1, 1.0), (37, 53, 41, 0.2), (300, 300, 300, 0.03),
+                                        (2000, 1500, 1800, 0.01), (64, 4000, 64, 0.3)])
+def test_random_exact(ns, ctx, dtype, m, k, n, dens):
+    a, b = _rand(ns, m, k, dens, 1, dtype), _rand(ns, k, n, dens, 2, dtype)
+    _check(ns, ctx, a, b, exact_values=True)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_random_float_values_tolerance(ns, ctx, dtype):
+    a, b = _rand(ns, 3000, 3000, 0.002, 5, dtype, ints=False), _rand(ns, 3000, 3000, 0.002, 6, dtype, ints=False)
+    _check(ns, ctx, a, b)
+
+
+def test_empty_rows_and_empty_matrix(ns, ctx):
+    z = ns.CSR(5, 5, np.zeros(6, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float64))
+    c, got = _run(ns, ctx, z, z)
+    assert c.nnz == 0 and got[0].tolist() == [0] * 6
+    # rows 1 and 3 of A empty; column 2 of A hits an empty row of B
+    a = ns.CSR(4, 4, [0, 2, 2, 3, 3], [0, 2, 1], np.array([1.0, 2.0, 3.0]))
+    b = ns.CSR(4, 3, [0, 1, 3, 3, 3], [2, 0, 1], np.array([5.0, 6.0, 7.0]))
+    _check(ns, ctx, a, b, exact_values=True)
+    m0 = ns.CSR(0, 7, np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float32))
+    b7 = _rand(ns, 7, 9, 0.3, 3, np.float32)
+    c, got = _run(ns, ctx, m0, b7)
+    assert c.nnz == 0 and got[0].tolist() == [0]
+
+
+def test_numerical_zero_is_kept(ns, ctx):
+    a = ns.CSR(1, 2, [0, 2], [0, 1], np.array([1.0, -1.0]))
+    b = ns.CSR(2, 1, [0, 1, 2], [0, 0], np.array([1.0, 1.0]))
+    c, got = _run(ns, ctx, a, b)
+    assert got[0].tolist() == [0, 1] and got[1].tolist() == [0] and got[2].tolist() == [0.0]
+
+
+def test_unsorted_input_rows(ns, ctx):
+    """The reference reader emits unsorted rows for symmetric files (nsparse.cu:115-123)."""
+    a = _rand(ns, 400, 400, 0.03, 9, np.float64)
+    rng = np.random.default_rng(1)
+    col, val = a.col.copy(), a.val.copy()
+    for i in range(a.M):
+        s, e = a.rpt[i], a.rpt[i + 1]
+        p = rng.permutation(e - s)
+        col[s:e], val[s:e] = col[s:e][p], val[s:e][p]
+    u = ns.CSR(a.M, a.N, a.rpt, col, val)
+    _check(ns, ctx, u, u, exact_values=True)
+
+
+def _row_with(nprod, n, seed):
+    """A (1 x k) * B (k x n) whose single row has exactly `nprod` intermediate products."""
+    import nsparse_b200 as ns
+
+    rng = np.random.default_rng(seed)
+    nb = 16 if (nprod % 16 == 0 and nprod >= 64) else 1
+    la = nprod // nb
+    k = max(la, 64)
+    acol = np.sort(rng.choice(k, size=la, replace=False)).astype(np.int32)
+    a = ns.CSR(1, k, [0, la], acol, np.ones(la, np.float64))
+    bc = np.sort(rng.integers(0, n - nb, size=(k, nb)), axis=1) + np.arange(nb)   # distinct, sorted
+    b = ns.CSR(k, n, np.arange(k + 1, dtype=np.int32) * nb, bc.reshape(-1).astype(np.int32), np.ones(k * nb))
+    return a, b
+
+
+@pytest.mark.parametrize("nprod", [32, 33, 64, 512, 513, 1024, 4096, 4097, 8192, 16384, 16385, 32768, 40000])
+def test_symbolic_bin_boundaries(ns, ctx, nprod):
+    """Rows whose intermediate-product count sits on every class edge of the symbolic ladder
+    (reference edges 32/512/1024/2048/4096/8192, ours 32/512/4096/16384)."""
+    a, b = _row_with(nprod, 200000, nprod)
+    _check(ns, ctx, a, b, exact_values=True)
+
+
+@pytest.mark.parametrize("nnz_row", [16, 17, 256, 257, 2048, 2049, 8192, 8193, 20000])
+def test_numeric_bin_boundaries(ns, ctx, nnz_row):
+    """Rows whose nnz(C_i) sits exactly on every class edge of the numeric ladder: B = identity-like
+    so nnz(C_i) == nnz(A_i)."""
+    n = 30000
+    rng = np.random.default_rng(nnz_row)
+    acol = np.sort(rng.choice(n, size=nnz_row, replace=False)).astype(np.int32)
+    a = ns.CSR(2, n, [0, nnz_row, nnz_row + 1], np.concatenate([acol, [5]]).astype(np.int32),
+               rng.integers(1, 5, nnz_row + 1).astype(np.float64))
+    b = ns.CSR(n, n, np.arange(n + 1, dtype=np.int32), np.arange(n, dtype=np.int32), np.full(n, 2.0))
+    c, got = _check(ns, ctx, a, b, exact_values=True)
+    assert got[0].tolist() == [0, nnz_row, nnz_row + 1]
+
+
+@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_all_lane_widths_and_forced_bitmap(ns, dtype, lanes):
+    """Every lanes-per-B-row instantiation, with the bitmap kernels forced on for all rows above
+    the 4-thread class, must agree with the hash kernels and the oracle."""
+    a = _rand(ns, 1500, 1200, 0.02, 21, dtype)
+    b = _rand(ns, 1200, 5000, 0.01, 22, dtype)
+    want = _oracle(a, b)
+    for force in (False, True):
+        c2 = ns.Context(0)
+        c2.set_option("lanes_per_brow", lanes)
+        if force:
+            c2.set_option("sym_bitmap_min", 32)
+            c2.set_option("num_bitmap_min", 16)
+        _, got = _run(ns, c2, a, b)
+        ok, msg = oracle.check_spgemm_answer(got, want)
+        assert ok, f"lanes={lanes} force_bitmap={force}: {msg}"
+        assert np.array_equal(got[2], want[2])
+        c2.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_rmat_scale14(ns, ctx, dtype):
+    """Small sibling of config C2 (heavy-tailed rows exercise every class incl. the bitmap kernels)."""
+    from nsparse_b200 import gen
+
+    a = gen.rmat_csr(14, 16, seed=12345, dtype=dtype, values="small_int")
+    c, got = _check(ns, ctx, a, a, exact_values=True)
+    assert c.nnz > 10 * a.nnz
+
+
+def test_wide_matrix_multi_tile_bitmap(ns):
+    """N larger than one bitmap tile (symbolic tile ~1.85 M columns, numeric ~1.23 M): heavy rows
+    take several column passes."""
+    n = 4_000_000
+    rng = np.random.default_rng(4)
+    la = 3000
+    acol = np.sort(rng.choice(5000, size=la, replace=False)).astype(np.int32)
+    a = ns.CSR(3, 5000, [0, la, la + 2, la + 2], np.concatenate([acol, [1, 7]]).astype(np.int32),
+               rng.integers(1, 3, la + 2).astype(np.float64))
+    bc = np.sort(rng.integers(0, n, size=(5000, 12)), axis=1)
+    bc[:, 1:] = np.where(bc[:, 1:] <= bc[:, :-1], bc[:, :-1] + 1, bc[:, 1:])
+    bc = np.minimum(bc, n - 1)
+    keep = np.ones_like(bc, bool)
+    keep[:, 1:] = bc[:, 1:] > bc[:, :-1]
+    rpt = np.zeros(5001, np.int32)
+    rpt[1:] = np.cumsum(keep.sum(axis=1))
+    b = ns.CSR(5000, n, rpt, bc[keep].astype(np.int32), np.ones(int(rpt[-1])))
+    c2 = ns.Context(0)
+    _check(ns, c2, a, b, exact_values=True)
+    c2.close()
+
+
+def test_rpt32_narrowing_and_overflow_guard(ns, ctx):
+    import ctypes as C
+
+    import torch
+
+    a = _rand(ns, 100, 100, 0.1, 1, np.float32)
+    c, got = _run(ns, ctx, a, a)
+    r32 = torch.empty(a.M + 1, dtype=torch.int32, device="cuda")
+    ctx.check(ctx.lib.nsp_rpt64_to_rpt32(ctx.handle, a.M, C.c_void_p(c.d_rpt64.data_ptr()), c.nnz,
+                                         C.c_void_p(r32.data_ptr())))
+    ctx.sync()
+    assert np.array_equal(r32.cpu().numpy().astype(np.int64), got[0])
+    rc = ctx.lib.nsp_rpt64_to_rpt32(ctx.handle, a.M, C.c_void_p(c.d_rpt64.data_ptr()), 2 ** 31,
+                                    C.c_void_p(r32.data_ptr()))
+    assert rc == -3   # NSP_ERR_OVERFLOW instead of the reference's silent wrap
+
+
+def test_host_buffer_entry_point(ns, ctx):
+    """nsp_spgemm_host_*: host CSR in, device result fetched into host arrays."""
+    import ctypes as C
+
+    a = _rand(ns, 500, 400, 0.03, 31, np.float64)
+    b = _rand(ns, 400, 600, 0.03, 32, np.float64)
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    nnz = C.c_longlong()
+    ctx.check(ctx.lib.nsp_spgemm_host_d(ctx.handle, a.M, a.N, b.N, p(a.rpt), p(a.col), p(a.val), p(b.rpt),
+                                        p(b.col), p(b.val), C.byref(nnz)))
+    want = _oracle(a, b)
+    assert nnz.value == int(want[0][-1])
+    rpt = np.empty(a.M + 1, np.int64)
+    col = np.empty(nnz.value, np.int32)
+    val = np.empty(nnz.value, np.float64)
+    ctx.check(ctx.lib.nsp_spgemm_host_fetch_d(ctx.handle, p(rpt), p(col), p(val)))
+    ok, msg = oracle.check_spgemm_answer((rpt, col, val), want)
+    assert ok, msg
+    ctx.check(ctx.lib.nsp_spgemm_host_release(ctx.handle))
