@@ -41,6 +41,7 @@ SIGNATURES = {
     "nsp_sync": (C.c_int, [vp]),
     "nsp_set_option": (C.c_int, [vp, C.c_char_p, ll]),
     "nsp_launch_count": (ll, [vp]),
+    "nsp_profile_dump": (C.c_int, [vp, C.c_char_p, C.c_size_t]),
     "nsp_spgemm_flop": (C.c_int, [vp, C.c_int, vp, vp, vp, C.POINTER(ll)]),
     "nsp_spgemm_symbolic": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp,
                                       C.POINTER(ll), C.POINTER(ll)]),

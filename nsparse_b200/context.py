@@ -43,6 +43,19 @@ class Context:
     def launches(self) -> int:
         return int(self.lib.nsp_launch_count(self.handle))
 
+    def profile(self, on: bool = True):
+        self.set_option("profile", 1 if on else 0)
+
+    def profile_dump(self):
+        """[(kernel, ms, rows, intermediate products, A entries)] of the launches since the last dump."""
+        buf = C.create_string_buffer(1 << 16)
+        self.check(self.lib.nsp_profile_dump(self.handle, buf, len(buf)))
+        out = []
+        for line in buf.value.decode().splitlines():
+            n, ms, rows, ip, alen = line.split()
+            out.append((n, float(ms), int(rows), int(ip), int(alen)))
+        return out
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.nsp_destroy(self.handle)

@@ -38,6 +38,7 @@ int nsp_set_option(nsp_context *ctx, const char *name, long long value)
     if (!ctx || !name) return NSP_ERR_ARG;
     if (!strcmp(name, "sym_bitmap_min")) ctx->opt_sym_bitmap_min = value;
     else if (!strcmp(name, "num_bitmap_min")) ctx->opt_num_bitmap_min = value;
+    else if (!strcmp(name, "profile")) ctx->profile = value != 0;
     else if (!strcmp(name, "lanes_per_brow")) {
         if (value != 0 && value != 4 && value != 8 && value != 16 && value != 32)
             return ctx->fail(NSP_ERR_ARG, "lanes_per_brow must be 0, 4, 8, 16 or 32");
@@ -48,6 +49,29 @@ int nsp_set_option(nsp_context *ctx, const char *name, long long value)
 }
 
 long long nsp_launch_count(nsp_context *ctx) { return ctx ? ctx->launches : 0; }
+
+int nsp_profile_dump(nsp_context *ctx, char *buf, size_t buflen)
+{
+    NSP_REQUIRE_CTX(ctx);
+    NSP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    std::string out;
+    for (auto &r : ctx->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        char line[256];
+        snprintf(line, sizeof(line), "%s %.6f %lld %lld %lld\n", r.name.c_str(), ms, r.rows, r.ip, r.alen);
+        out += line;
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    ctx->prof.clear();
+    if (buf && buflen) {
+        const size_t n = out.size() < buflen - 1 ? out.size() : buflen - 1;
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return 0;
+}
 
 // ---- SpGEMM, device pointers ---------------------------------------------------------------
 int nsp_spgemm_flop(nsp_context *ctx, int M, const int *d_a_rpt, const int *d_a_col, const int *d_b_rpt,

@@ -41,6 +41,12 @@ struct nsp_host_result {
     int in_val_bytes = 0;
 };
 
+struct nsp_prof_rec {
+    std::string name;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    long long rows = 0, ip = 0, alen = 0;
+};
+
 struct nsp_context {
     int device = 0;
     cudaStream_t stream = nullptr;   // nullptr = legacy default stream
@@ -63,6 +69,28 @@ struct nsp_context {
 
     long long launches = 0;
     std::string err;
+
+    // per-launch CUDA-event timing of the row-class kernels (nsp_set_option("profile", 1))
+    bool profile = false;
+    std::vector<nsp_prof_rec> prof;
+    void prof_begin(const char *name, long long rows, long long ip, long long alen)
+    {
+        if (!profile) return;
+        nsp_prof_rec r;
+        r.name = name;
+        r.rows = rows;
+        r.ip = ip;
+        r.alen = alen;
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, stream);
+        prof.push_back(r);
+    }
+    void prof_end()
+    {
+        if (!profile || prof.empty()) return;
+        cudaEventRecord(prof.back().e1, stream);
+    }
 
     int fail(int code, const std::string &msg)
     {

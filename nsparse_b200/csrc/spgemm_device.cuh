@@ -6,64 +6,130 @@
 
 namespace nsp {
 
+// group-wide barrier: a warp (GROUP == 32, several rows per CTA) or the whole CTA
+template <int GROUP>
+__device__ __forceinline__ void group_sync()
+{
+    if (GROUP == 32)
+        __syncwarp();
+    else
+        __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------------
-// Row traversal.  A "group" of GT threads owns one row of C.  It is split into sub-groups of LB
-// lanes; each sub-group takes one entry a_ij of the A row at a time and strides the B row j with
-// its LB lanes, so loads of B.col / B.val are coalesced runs of LB elements.  LB is picked on the
-// host from the mean B-row length seen by the class (long rows: 32, ER-like 4-nnz rows: 4).
-// The (column, rpt pair) of the NEXT A entry is fetched before the current B row is walked so
-// the dependent a_col -> b_rpt -> b_col chain of the reference (kernel_spgemm_hash_d.cu:427-430)
-// is overlapped with the probe loop, and the B row is read four strides at a time.
-// f(col, value) is called once per intermediate product.
+// Row traversal -- load-balanced over PRODUCTS, not over A entries.
+//
+// A "group" of GROUP threads (a warp or a CTA) owns one row i of C.  The reference gives every
+// warp one entry a_ij and lets its lanes stride the B row j (kernel_spgemm_hash_d.cu:427-430):
+// on heavy-tailed inputs one warp then walks a 40 000-entry B row alone while 31 warps idle
+// (measured here: 1.1 G products/s for the 1024-thread classes on R-MAT scale 20).  Instead the
+// group stages a slab of up to GROUP entries of the A row in shared memory as
+//     s_kb[e]  = B.rpt[a_col[e]]            first product of entry e in B.col / B.val
+//     s_pre[e] = sum_{e' < e} nnz(B_{a_col[e']})   (exclusive scan; s_pre[GROUP] = slab total)
+//     s_av[e]  = a_val[e]                   (numeric only)
+// and then walks the slab's products p = 0 .. total-1 with stride GROUP: thread t finds its entry
+// by a branch-free binary search over s_pre (log2(GROUP) shared-memory reads, mostly broadcasts)
+// and reads B.col[s_kb[e] + p - s_pre[e]].  Consecutive lanes hit consecutive addresses inside a
+// B row, every lane has work whatever the B-row length distribution, and four products per thread
+// are in flight before the first table update.  f(col, value) is called once per product.
 // ---------------------------------------------------------------------------------------------
-template <int GT, int LB, bool kNumeric, typename real, typename F>
+template <int GROUP, typename real>
+struct FlatScratch {
+    int pre[GROUP + 1];
+    int kb[GROUP];
+    real av[GROUP];
+    int wtot[GROUP / 32 + 1];
+};
+
+template <int GROUP>
+__device__ __forceinline__ int group_inclusive_scan(int v, int t, int *wtot)
+{
+    const int lane = t & 31;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int x = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += x;
+    }
+    if (GROUP > 32) {
+        const int wid = t >> 5;
+        if (lane == 31) wtot[wid] = inc;
+        __syncthreads();
+        int add = 0;
+        for (int w = 0; w < wid; ++w) add += wtot[w];
+        inc += add;
+    }
+    return inc;
+}
+
+template <int GROUP, bool kNumeric, typename real, typename F>
 __device__ __forceinline__ void for_each_product(int t, int a_beg, int a_end,
                                                  const int *__restrict__ a_col,
                                                  const real *__restrict__ a_val,
                                                  const int *__restrict__ b_rpt,
                                                  const int *__restrict__ b_col,
-                                                 const real *__restrict__ b_val, F &&f)
+                                                 const real *__restrict__ b_val,
+                                                 FlatScratch<GROUP, real> &s, F &&f)
 {
-    constexpr int NSG = GT / LB;
     constexpr int U = 4;
-    const int sg = t / LB, sl = t % LB;
-    int j = a_beg + sg;
-    int kb = 0, ke = 0;
-    real av = real(0);
-    if (j < a_end) {
-        const int ac = ld_stream(a_col + j);
-        if (kNumeric) av = ld_stream(a_val + j);
-        kb = ld_nc(b_rpt + ac);
-        ke = ld_nc(b_rpt + ac + 1);
-    }
-    while (j < a_end) {
-        const int jn = j + NSG;
-        int kbn = 0, ken = 0;
-        real avn = real(0);
-        if (jn < a_end) {
-            const int ac = ld_stream(a_col + jn);
-            if (kNumeric) avn = ld_stream(a_val + jn);
-            kbn = ld_nc(b_rpt + ac);
-            ken = ld_nc(b_rpt + ac + 1);
+    for (int base = a_beg; base < a_end; base += GROUP) {
+        int len = 0, kb = 0;
+        if (base + t < a_end) {
+            const int ac = ld_stream(a_col + base + t);
+            kb = ld_nc(b_rpt + ac);
+            len = ld_nc(b_rpt + ac + 1) - kb;
+            if (kNumeric) s.av[t] = ld_stream(a_val + base + t);
         }
-        for (int k = kb + sl; k < ke; k += U * LB) {
+        s.kb[t] = kb;
+        const int inc = group_inclusive_scan<GROUP>(len, t, s.wtot);
+        s.pre[t + 1] = inc;
+        if (t == 0) s.pre[0] = 0;
+        group_sync<GROUP>();
+        const int total = s.pre[GROUP];
+        // Every warp takes contiguous chunks of 32*U products.  The entry owning the first product
+        // of a chunk is found ONCE per chunk by a cooperative 32-ary search (two ballots); the lanes
+        // then only advance monotonically, keeping the current entry's bounds in registers.  This
+        // costs ~1 compare per product on long B rows (a per-product binary search made the
+        // kernels issue-bound at ~100 warp instructions per product: profiles/r1_*).
+        constexpr int S1 = GROUP / 32;       // level-1 stride of the 32-ary search
+        const int lane = t & 31;
+        for (int base_p = (t >> 5) * (32 * U); base_p < total; base_p += GROUP * U) {
+            int e = 0;
+            {
+                const unsigned q1 = __ballot_sync(0xffffffffu, s.pre[lane * S1] <= base_p);
+                e = (__popc(q1) - 1) * S1;
+                if (S1 > 1) {
+                    const unsigned q2 = __ballot_sync(0xffffffffu, lane < S1 && s.pre[e + lane] <= base_p);
+                    e += __popc(q2) - 1;
+                }
+            }
+            int next = s.pre[e + 1];
+            int koff = s.kb[e] - s.pre[e];
+            real av = kNumeric ? s.av[e] : real(0);
             int c[U];
             real v[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int kk = k + u * LB;
-                c[u] = kk < ke ? ld_nc(b_col + kk) : -1;
-                if (kNumeric) v[u] = kk < ke ? ld_nc(b_val + kk) : real(0);
+                const int p = base_p + u * 32 + lane;
+                c[u] = -1;
+                if (p < total) {
+                    if (p >= next) {
+                        do {
+                            ++e;
+                            next = s.pre[e + 1];
+                        } while (p >= next);
+                        koff = s.kb[e] - s.pre[e];
+                        if (kNumeric) av = s.av[e];
+                    }
+                    c[u] = ld_nc(b_col + koff + p);
+                    if (kNumeric) v[u] = av * ld_nc(b_val + koff + p);
+                }
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (c[u] >= 0) f(c[u], kNumeric ? av * v[u] : real(0));
-            }
+            for (int u = 0; u < U; ++u)
+                if (c[u] >= 0) f(c[u], kNumeric ? v[u] : real(0));
         }
-        j = jn;
-        kb = kbn;
-        ke = ken;
-        av = avn;
+        group_sync<GROUP>();
     }
 }
 
@@ -102,16 +168,6 @@ __device__ __forceinline__ void hash_accumulate(int *keys, real *vals, unsigned 
         h = (h + 1) & mask;
     }
     atomicAdd(vals + h, v);
-}
-
-// group-wide barrier: a warp (GROUP == 32, several rows per CTA) or the whole CTA
-template <int GROUP>
-__device__ __forceinline__ void group_sync()
-{
-    if (GROUP == 32)
-        __syncwarp();
-    else
-        __syncthreads();
 }
 
 // Bitonic sort of n (power of two) (key, value) slots by unsigned key, so that the free slots

@@ -81,7 +81,7 @@ num_pwarp_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
 }
 
 // ---- hash classes -------------------------------------------------------------------------------
-template <typename real, int GROUP, int BS, int LB>
+template <typename real, int GROUP, int BS>
 __global__ void __launch_bounds__(BS, (BS >= 1024 ? 1 : 2))
 num_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                 const real *__restrict__ a_val, const int *__restrict__ b_rpt,
@@ -91,9 +91,9 @@ num_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                 int queue, int tmax)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_row;
     constexpr int NG = BS / GROUP;
-    constexpr int LBE = LB < GROUP ? LB : GROUP;
+    __shared__ FlatScratch<GROUP, real> s_flat[NG];
+    __shared__ int s_row;
     const int g = threadIdx.x / GROUP, t = threadIdx.x % GROUP;
     // values first (8-byte aligned for fp64), then keys
     real *vals = reinterpret_cast<real *>(smem_raw) + (size_t)g * tmax;
@@ -123,9 +123,9 @@ num_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
             vals[i] = real(0);
         }
         group_sync<GROUP>();
-        for_each_product<GROUP, LBE, true, real>(
-            t, a_rpt[rid], a_rpt[rid + 1], a_col, a_val, b_rpt, b_col, b_val,
-            [&](int c, real v) { hash_accumulate(keys, vals, mask, c, v); });
+        for_each_product<GROUP, true, real>(t, a_rpt[rid], a_rpt[rid + 1], a_col, a_val, b_rpt, b_col, b_val,
+                                            s_flat[g],
+                                            [&](int c, real v) { hash_accumulate(keys, vals, mask, c, v); });
         group_sync<GROUP>();
         bitonic_sort_slots<GROUP, real>(keys, vals, tsize, t);
         for (int i = t; i < nnz; i += GROUP) {
@@ -138,8 +138,8 @@ num_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
 
 // ---- bitmap + rank class ------------------------------------------------------------------------
 // shared memory: bm[nw] 64-bit bitmap words of the column tile, pre[nw] exclusive popcount prefix
-template <typename real, int BS, int LB>
-__global__ void __launch_bounds__(BS, (BS >= 1024 ? 1 : 2))
+template <typename real, int BS>
+__global__ void __launch_bounds__(BS, 1)
 num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                   const real *__restrict__ a_val, const int *__restrict__ b_rpt,
                   const int *__restrict__ b_col, const real *__restrict__ b_val,
@@ -148,6 +148,7 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                   int queue, int N, int tile_cols)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ FlatScratch<BS, real> s_flat;
     __shared__ int s_row;
     __shared__ int s_warp[BS / 32];
     __shared__ int s_carry;
@@ -174,8 +175,8 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
             if (t == 0) s_carry = 0;
             __syncthreads();
             // pass 1: structure of the tile
-            for_each_product<BS, LB, false, real>(
-                t, a_beg, a_end, a_col, a_val, b_rpt, b_col, b_val, [&](int c, real) {
+            for_each_product<BS, false, real>(
+                t, a_beg, a_end, a_col, a_val, b_rpt, b_col, b_val, s_flat, [&](int c, real) {
                     const unsigned cc = (unsigned)(c - t0);
                     if (cc < (unsigned)ncols) {
                         const unsigned bit = 1u << (cc & 31);
@@ -228,13 +229,12 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
             }
             __syncthreads();
             // pass 2: values
-            for_each_product<BS, LB, true, real>(
-                t, a_beg, a_end, a_col, a_val, b_rpt, b_col, b_val, [&](int c, real v) {
+            for_each_product<BS, true, real>(
+                t, a_beg, a_end, a_col, a_val, b_rpt, b_col, b_val, s_flat, [&](int c, real v) {
                     const unsigned cc = (unsigned)(c - t0);
                     if (cc < (unsigned)ncols) {
                         const unsigned w = cc >> 6;
-                        const int rank =
-                            pre[w] + __popcll(bm[w] & ((1ull << (cc & 63)) - 1ull));
+                        const int rank = pre[w] + __popcll(bm[w] & ((1ull << (cc & 63)) - 1ull));
                         atomicAdd(c_val + out + rank, v);
                     }
                 });
@@ -247,21 +247,6 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static inline int num_lanes_for(const nsp_context *ctx, const nsp_spgemm_state &sp, int bin_lo, int bin_hi)
-{
-    if (ctx->opt_lanes_per_brow > 0) return (int)ctx->opt_lanes_per_brow;
-    unsigned long long ip = 0, len = 0;
-    for (int b = bin_lo; b <= bin_hi; ++b) {
-        ip += sp.h_binsum[kSumIp + b];
-        len += sp.h_binsum[kSumLen + b];
-    }
-    const double avg = len ? (double)ip / (double)len : 0.0;
-    if (avg >= 24.0) return 32;
-    if (avg >= 12.0) return 16;
-    if (avg >= 6.0) return 8;
-    return 4;
-}
-
 static inline long long num_rows_in(const nsp_spgemm_state &sp, int bin_lo, int bin_hi)
 {
     long long n = 0;
@@ -271,56 +256,33 @@ static inline long long num_rows_in(const nsp_spgemm_state &sp, int bin_lo, int 
 
 static inline int num_imin(long long a, long long b) { return (int)(a < b ? a : b); }
 
+static inline void num_prof_class(nsp_context *ctx, const char *name, int bin_lo, int bin_hi)
+{
+    if (!ctx->profile) return;
+    long long rows = 0, ip = 0, len = 0;
+    for (int b = bin_lo; b <= bin_hi; ++b) {
+        rows += ctx->sp.h_bins[kBinHist + b];
+        ip += (long long)ctx->sp.h_binsum[kSumIp + b];
+        len += (long long)ctx->sp.h_binsum[kSumLen + b];
+    }
+    ctx->prof_begin(name, rows, ip, len);
+}
+
 #define NSP_NUM_ARGS                                                                               \
     a_rpt, a_col, a_val, b_rpt, b_col, b_val, c_rpt64, c_col, c_val, sp.d_row_perm, sp.d_bins
 
 template <typename real, int GROUP, int BS>
-static int launch_num_hash(nsp_context *ctx, int lanes, int grid, size_t smem, const int *a_rpt,
+static int launch_num_hash(nsp_context *ctx, const char *name, int grid, size_t smem, const int *a_rpt,
                            const int *a_col, const real *a_val, const int *b_rpt, const int *b_col,
                            const real *b_val, const long long *c_rpt64, int *c_col, real *c_val,
                            int bin_lo, int bin_hi, int queue, int tmax)
 {
     nsp_spgemm_state &sp = ctx->sp;
-#define NSP_NUM_LAUNCH(LBV)                                                                        \
-    {                                                                                              \
-        auto kern = num_hash_kernel<real, GROUP, BS, LBV>;                                         \
-        NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                               (int)smem));                                        \
-        kern<<<grid, BS, smem, ctx->stream>>>(NSP_NUM_ARGS, bin_lo, bin_hi, queue, tmax);          \
-    }
-    switch (lanes) {
-        case 4: NSP_NUM_LAUNCH(4) break;
-        case 8: NSP_NUM_LAUNCH(8) break;
-        case 16: NSP_NUM_LAUNCH(16) break;
-        default: NSP_NUM_LAUNCH(32) break;
-    }
-#undef NSP_NUM_LAUNCH
-    ctx->launches += 1;
-    NSP_CUDA_TRY(ctx, cudaGetLastError());
-    return 0;
-}
-
-template <typename real>
-static int launch_num_bitmap(nsp_context *ctx, int lanes, int grid, size_t smem, const int *a_rpt,
-                             const int *a_col, const real *a_val, const int *b_rpt, const int *b_col,
-                             const real *b_val, const long long *c_rpt64, int *c_col, real *c_val,
-                             int bin_lo, int bin_hi, int queue, int N, int tile_cols)
-{
-    nsp_spgemm_state &sp = ctx->sp;
-#define NSP_NUM_LAUNCH(LBV)                                                                        \
-    {                                                                                              \
-        auto kern = num_bitmap_kernel<real, 1024, LBV>;                                            \
-        NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                               (int)smem));                                        \
-        kern<<<grid, 1024, smem, ctx->stream>>>(NSP_NUM_ARGS, bin_lo, bin_hi, queue, N, tile_cols); \
-    }
-    switch (lanes) {
-        case 4: NSP_NUM_LAUNCH(4) break;
-        case 8: NSP_NUM_LAUNCH(8) break;
-        case 16: NSP_NUM_LAUNCH(16) break;
-        default: NSP_NUM_LAUNCH(32) break;
-    }
-#undef NSP_NUM_LAUNCH
+    auto kern = num_hash_kernel<real, GROUP, BS>;
+    NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    num_prof_class(ctx, name, bin_lo, bin_hi);
+    kern<<<grid, BS, smem, ctx->stream>>>(NSP_NUM_ARGS, bin_lo, bin_hi, queue, tmax);
+    ctx->prof_end();
     ctx->launches += 1;
     NSP_CUDA_TRY(ctx, cudaGetLastError());
     return 0;
@@ -343,14 +305,16 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
     //   bins 5..7      <= 2048      CTA(256) / row, <= 4096 slots
     //   bins 8..9      <= 8192      CTA(1024) / row, <= 16384 slots (128 KiB fp32 / 192 KiB fp64)
     //   bins >= bm_bin              CTA(1024) / row, bitmap + rank over column tiles
-    const int smem_cap = ctx->max_smem_optin - 2048;
+    const int smem_cap = ctx->max_smem_optin - kStaticSmemReserve;
     const int tile_max = (smem_cap / 12) * 64;
     const int tile_cols = N < tile_max ? ((N + 63) / 64) * 64 : tile_max;
     const int slot_bytes = 4 + (int)sizeof(real);
     int bm_bin = 10;
     if (N <= tile_max) {
-        const int v = (int)((long long)N * 9 / (64ll * slot_bytes)) + 1;
-        bm_bin = log_bin(v, kNumShift);
+        // single tile: bitmap + rank needs no sort, the hash path pays an O(n log^2 n) bitonic sort
+        // per row; measured crossover on R-MAT ~N/1024 entries per row
+        const int v = N / 1024 + 1;
+        bm_bin = log_bin(v, kNumShift) + 1;
         if (bm_bin < 5) bm_bin = 5;
         if (bm_bin > 10) bm_bin = 10;
     }
@@ -362,44 +326,46 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
     const int sms = ctx->sm_count;
     if (num_rows_in(sp, bm_bin, kNumBins - 1) > 0) {
         const size_t smem = (size_t)(tile_cols / 64) * 12;
-        const int per_sm = (smem + 2048) * 2 <= (size_t)ctx->max_smem_optin ? 2 : 1;
-        const int grid = num_imin(num_rows_in(sp, bm_bin, kNumBins - 1), (long long)sms * per_sm);
-        if (launch_num_bitmap<real>(ctx, num_lanes_for(ctx, sp, bm_bin, kNumBins - 1), grid, smem, a_rpt,
-                                    a_col, a_val, b_rpt, b_col, b_val, c_rpt64, c_col, c_val, bm_bin,
-                                    kNumBins - 1, 4, N, tile_cols) != 0)
-            return -1;
+        const int grid = num_imin(num_rows_in(sp, bm_bin, kNumBins - 1), (long long)sms);
+        auto kern = num_bitmap_kernel<real, 1024>;
+        NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        num_prof_class(ctx, "num_bitmap", bm_bin, kNumBins - 1);
+        kern<<<grid, 1024, smem, ctx->stream>>>(NSP_NUM_ARGS, bm_bin, kNumBins - 1, 4, N, tile_cols);
+        ctx->prof_end();
+        ctx->launches += 1;
+        NSP_CUDA_TRY(ctx, cudaGetLastError());
     }
     if (bm_bin > 8 && num_rows_in(sp, 8, num_imin(9, bm_bin - 1)) > 0) {
         const int hi = num_imin(9, bm_bin - 1);
         const int tmax = 16384;
         const int grid = num_imin(num_rows_in(sp, 8, hi), sms);
-        if (launch_num_hash<real, 1024, 1024>(ctx, num_lanes_for(ctx, sp, 8, hi), grid,
-                                              (size_t)tmax * slot_bytes, a_rpt, a_col, a_val, b_rpt, b_col,
-                                              b_val, c_rpt64, c_col, c_val, 8, hi, 3, tmax) != 0)
+        if (launch_num_hash<real, 1024, 1024>(ctx, "num_hash_cta1024", grid, (size_t)tmax * slot_bytes, a_rpt,
+                                              a_col, a_val, b_rpt, b_col, b_val, c_rpt64, c_col, c_val, 8, hi, 3,
+                                              tmax) != 0)
             return -1;
     }
     if (bm_bin > 5 && num_rows_in(sp, 5, num_imin(7, bm_bin - 1)) > 0) {
         const int hi = num_imin(7, bm_bin - 1);
         const int tmax = 4096;
         const int grid = num_imin(num_rows_in(sp, 5, hi), (long long)sms * 4);
-        if (launch_num_hash<real, 256, 256>(ctx, num_lanes_for(ctx, sp, 5, hi), grid,
-                                            (size_t)tmax * slot_bytes, a_rpt, a_col, a_val, b_rpt, b_col,
-                                            b_val, c_rpt64, c_col, c_val, 5, hi, 2, tmax) != 0)
+        if (launch_num_hash<real, 256, 256>(ctx, "num_hash_cta256", grid, (size_t)tmax * slot_bytes, a_rpt, a_col,
+                                            a_val, b_rpt, b_col, b_val, c_rpt64, c_col, c_val, 5, hi, 2, tmax) != 0)
             return -1;
     }
     if (num_rows_in(sp, 1, num_imin(4, bm_bin - 1)) > 0) {
         const int hi = num_imin(4, bm_bin - 1);
         const int tmax = 512;
         const int grid = num_imin((num_rows_in(sp, 1, hi) + 7) / 8, (long long)sms * 4);
-        if (launch_num_hash<real, 32, 256>(ctx, num_lanes_for(ctx, sp, 1, hi), grid,
-                                           (size_t)tmax * slot_bytes * 8, a_rpt, a_col, a_val, b_rpt, b_col,
-                                           b_val, c_rpt64, c_col, c_val, 1, hi, 1, tmax) != 0)
+        if (launch_num_hash<real, 32, 256>(ctx, "num_hash_warp", grid, (size_t)tmax * slot_bytes * 8, a_rpt, a_col,
+                                           a_val, b_rpt, b_col, b_val, c_rpt64, c_col, c_val, 1, hi, 1, tmax) != 0)
             return -1;
     }
     if (num_rows_in(sp, 0, 0) > 0) {
         const int grid = num_imin((num_rows_in(sp, 0, 0) + 63) / 64, (long long)sms * 8);
+        num_prof_class(ctx, "num_pwarp", 0, 0);
         num_pwarp_kernel<real><<<grid, 256, 0, ctx->stream>>>(a_rpt, a_col, a_val, b_rpt, b_col, b_val,
                                                               c_rpt64, c_col, c_val, sp.d_row_perm, sp.d_bins);
+        ctx->prof_end();
         ctx->launches += 1;
         NSP_CUDA_TRY(ctx, cudaGetLastError());
     }

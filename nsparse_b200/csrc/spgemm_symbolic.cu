@@ -10,10 +10,11 @@
 //   * rows above the hash ladder use a shared-memory BITMAP over a column tile instead of the
 //     try-then-redo pair each_tb_large / each_gl (:474-622) whose global table needs
 //     fail_count * max_intprod ints.  Bits are tested before the atomicOr, so the atomic count is
-//     nnz(C_i), not the number of products.  Columns beyond one tile (N > ~1.8 M) take one pass
+//     nnz(C_i), not the number of products.  Columns beyond one tile (N > ~1.7 M) take one pass
 //     per tile; memory use is fixed and there is no failure path.
-//   * persistent CTAs pull rows from a queue ordered heaviest-first (no tail from 9.7 M-product
-//     rows landing last); no warp-synchronous assumptions: every phase boundary is a barrier.
+//   * products of a row are spread evenly over the threads (spgemm_device.cuh), whatever the
+//     B-row lengths; persistent CTAs pull rows from a queue ordered heaviest-first; no
+//     warp-synchronous assumptions: every phase boundary is a barrier.
 #include "context.h"
 #include "spgemm_device.cuh"
 #include "spgemm_plan.h"
@@ -59,7 +60,7 @@ sym_pwarp_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
 }
 
 // ---- hash classes: a group (warp or CTA) per row, table of `tmax` keys per group -----------------
-template <int GROUP, int BS, int LB>
+template <int GROUP, int BS>
 __global__ void __launch_bounds__(BS, (BS >= 1024 ? 1 : 2))
 sym_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                 const int *__restrict__ b_rpt, const int *__restrict__ b_col,
@@ -68,8 +69,9 @@ sym_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                 int tmax)
 {
     extern __shared__ int smem_i[];
+    constexpr int NG = BS / GROUP;
+    __shared__ FlatScratch<GROUP, float> s_flat[NG];
     __shared__ int s_row, s_cnt;
-    constexpr int LBE = LB < GROUP ? LB : GROUP;
     const int g = threadIdx.x / GROUP, t = threadIdx.x % GROUP;
     int *tab = smem_i + g * tmax;
     int lo, hi;
@@ -96,9 +98,9 @@ sym_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
         for (int i = t; i < tsize; i += GROUP) tab[i] = kEmptyKey;
         group_sync<GROUP>();
         int cnt = 0;
-        for_each_product<GROUP, LBE, false, float>(
+        for_each_product<GROUP, false, float>(
             t, a_rpt[rid], a_rpt[rid + 1], a_col, (const float *)nullptr, b_rpt, b_col,
-            (const float *)nullptr, [&](int c, float) { cnt += hash_insert_key(tab, mask, c); });
+            (const float *)nullptr, s_flat[g], [&](int c, float) { cnt += hash_insert_key(tab, mask, c); });
         cnt = warp_sum(cnt);
         if (GROUP == 32) {
             if (t == 0) row_cnt[rid] = cnt;
@@ -113,8 +115,8 @@ sym_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
 }
 
 // ---- bitmap class: one CTA per row, one pass over the row's products per column tile -------------
-template <int BS, int LB>
-__global__ void __launch_bounds__(BS, (BS >= 1024 ? 1 : 2))
+template <int BS>
+__global__ void __launch_bounds__(BS, 1)
 sym_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                   const int *__restrict__ b_rpt, const int *__restrict__ b_col,
                   const int *__restrict__ row_perm, int *__restrict__ row_cnt, int *__restrict__ bins,
@@ -122,6 +124,7 @@ sym_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
 {
     extern __shared__ int smem_i[];
     unsigned *bm = reinterpret_cast<unsigned *>(smem_i);
+    __shared__ FlatScratch<BS, float> s_flat;
     __shared__ int s_row, s_cnt;
     const int t = threadIdx.x;
     int lo, hi;
@@ -142,8 +145,8 @@ sym_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
             const int nw = (ncols + 31) >> 5;
             for (int i = t; i < nw; i += BS) bm[i] = 0u;
             __syncthreads();
-            for_each_product<BS, LB, false, float>(
-                t, a_beg, a_end, a_col, (const float *)nullptr, b_rpt, b_col, (const float *)nullptr,
+            for_each_product<BS, false, float>(
+                t, a_beg, a_end, a_col, (const float *)nullptr, b_rpt, b_col, (const float *)nullptr, s_flat,
                 [&](int c, float) {
                     const unsigned cc = (unsigned)(c - t0);
                     if (cc < (unsigned)ncols) {
@@ -166,19 +169,16 @@ sym_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int lanes_for(const nsp_context *ctx, const nsp_spgemm_state &sp, int bin_lo, int bin_hi)
+static void prof_class(nsp_context *ctx, const char *name, int bin_lo, int bin_hi)
 {
-    if (ctx->opt_lanes_per_brow > 0) return (int)ctx->opt_lanes_per_brow;
-    unsigned long long ip = 0, len = 0;
+    if (!ctx->profile) return;
+    long long rows = 0, ip = 0, len = 0;
     for (int b = bin_lo; b <= bin_hi; ++b) {
-        ip += sp.h_binsum[kSumIp + b];
-        len += sp.h_binsum[kSumLen + b];
+        rows += ctx->sp.h_bins[kBinHist + b];
+        ip += (long long)ctx->sp.h_binsum[kSumIp + b];
+        len += (long long)ctx->sp.h_binsum[kSumLen + b];
     }
-    const double avg = len ? (double)ip / (double)len : 0.0;
-    if (avg >= 24.0) return 32;
-    if (avg >= 12.0) return 16;
-    if (avg >= 6.0) return 8;
-    return 4;
+    ctx->prof_begin(name, rows, ip, len);
 }
 
 static long long rows_in(const nsp_spgemm_state &sp, int bin_lo, int bin_hi)
@@ -189,52 +189,17 @@ static long long rows_in(const nsp_spgemm_state &sp, int bin_lo, int bin_hi)
 }
 
 template <int GROUP, int BS>
-static int launch_sym_hash(nsp_context *ctx, int lanes, int grid, size_t smem, const int *a_rpt,
+static int launch_sym_hash(nsp_context *ctx, const char *name, int grid, size_t smem, const int *a_rpt,
                            const int *a_col, const int *b_rpt, const int *b_col, int bin_lo, int bin_hi,
                            int queue, int tmax)
 {
     nsp_spgemm_state &sp = ctx->sp;
-#define NSP_SYM_LAUNCH(LBV)                                                                         \
-    {                                                                                               \
-        auto kern = sym_hash_kernel<GROUP, BS, LBV>;                                                \
-        NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                               (int)smem));                                         \
-        kern<<<grid, BS, smem, ctx->stream>>>(a_rpt, a_col, b_rpt, b_col, sp.d_row_perm, sp.d_row_ip, \
-                                              sp.d_row_cnt, sp.d_bins, bin_lo, bin_hi, queue, tmax); \
-    }
-    switch (lanes) {
-        case 4: NSP_SYM_LAUNCH(4) break;
-        case 8: NSP_SYM_LAUNCH(8) break;
-        case 16: NSP_SYM_LAUNCH(16) break;
-        default: NSP_SYM_LAUNCH(32) break;
-    }
-#undef NSP_SYM_LAUNCH
-    ctx->launches += 1;
-    NSP_CUDA_TRY(ctx, cudaGetLastError());
-    return 0;
-}
-
-static int launch_sym_bitmap(nsp_context *ctx, int lanes, int grid, size_t smem, const int *a_rpt,
-                             const int *a_col, const int *b_rpt, const int *b_col, int bin_lo,
-                             int bin_hi, int queue, int N, int tile_cols)
-{
-    nsp_spgemm_state &sp = ctx->sp;
-#define NSP_SYM_LAUNCH(LBV)                                                                         \
-    {                                                                                               \
-        auto kern = sym_bitmap_kernel<1024, LBV>;                                                   \
-        NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                               (int)smem));                                         \
-        kern<<<grid, 1024, smem, ctx->stream>>>(a_rpt, a_col, b_rpt, b_col, sp.d_row_perm,          \
-                                                sp.d_row_cnt, sp.d_bins, bin_lo, bin_hi, queue, N,  \
-                                                tile_cols);                                         \
-    }
-    switch (lanes) {
-        case 4: NSP_SYM_LAUNCH(4) break;
-        case 8: NSP_SYM_LAUNCH(8) break;
-        case 16: NSP_SYM_LAUNCH(16) break;
-        default: NSP_SYM_LAUNCH(32) break;
-    }
-#undef NSP_SYM_LAUNCH
+    auto kern = sym_hash_kernel<GROUP, BS>;
+    NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_class(ctx, name, bin_lo, bin_hi);
+    kern<<<grid, BS, smem, ctx->stream>>>(a_rpt, a_col, b_rpt, b_col, sp.d_row_perm, sp.d_row_ip, sp.d_row_cnt,
+                                          sp.d_bins, bin_lo, bin_hi, queue, tmax);
+    ctx->prof_end();
     ctx->launches += 1;
     NSP_CUDA_TRY(ctx, cudaGetLastError());
     return 0;
@@ -261,14 +226,16 @@ int spgemm_symbolic(nsp_context *ctx, int M, int K, int N, const int *a_rpt, con
     //   bins 5..7      <= 4096      CTA(256) / row, <= 8192 slots (32 KiB)
     //   bins 8..9      <= 16384     CTA(1024) / row, <= 32768 slots (128 KiB)
     //   bins >= bm_bin              CTA(1024) / row, bitmap over column tiles
-    const int smem_cap = ctx->max_smem_optin - 1024;
+    const int smem_cap = ctx->max_smem_optin - kStaticSmemReserve;
     const int tile_max = (smem_cap / 4) * 32;                      // columns one bitmap tile can hold
     const int tile_cols = N < tile_max ? ((N + 31) / 32) * 32 : tile_max;
     int bm_bin = 10;
     if (N <= tile_max) {
-        // one tile covers the row: switch to the bitmap as soon as it is no bigger than the hash set
-        const int v = N / 43 + 1;
-        bm_bin = log_bin(v, kSymShift);
+        // one tile covers the row: clearing + counting the bitmap costs ~N/8 bytes of shared-memory
+        // traffic per row, the probe loop of the hash set costs per product; measured on R-MAT
+        // (scale 18/20, N = 2^18 / 2^20) the bitmap wins from ~N/512 products per row upwards
+        const int v = N / 512 + 1;
+        bm_bin = log_bin(v, kSymShift) + 1;
         if (bm_bin < 5) bm_bin = 5;
         if (bm_bin > 10) bm_bin = 10;
     }
@@ -281,42 +248,47 @@ int spgemm_symbolic(nsp_context *ctx, int M, int K, int N, const int *a_rpt, con
     if (M > 0) {
         // heaviest first
         if (rows_in(sp, bm_bin, kNumBins - 1) > 0) {
-            const int lanes = lanes_for(ctx, sp, bm_bin, kNumBins - 1);
             const size_t smem = (size_t)(tile_cols / 32) * 4;
-            const int per_sm = smem > 0 ? imin((size_t)smem_cap / (smem + 1024) , 2) : 2;
-            const int grid = imin(rows_in(sp, bm_bin, kNumBins - 1), (long long)sms * (per_sm < 1 ? 1 : per_sm));
-            if (launch_sym_bitmap(ctx, lanes, grid, smem, a_rpt, a_col, b_rpt, b_col, bm_bin, kNumBins - 1, 4,
-                                  N, tile_cols) != 0)
-                return -1;
+            const int grid = imin(rows_in(sp, bm_bin, kNumBins - 1), (long long)sms);
+            auto kern = sym_bitmap_kernel<1024>;
+            NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            prof_class(ctx, "sym_bitmap", bm_bin, kNumBins - 1);
+            kern<<<grid, 1024, smem, ctx->stream>>>(a_rpt, a_col, b_rpt, b_col, sp.d_row_perm, sp.d_row_cnt,
+                                                    sp.d_bins, bm_bin, kNumBins - 1, 4, N, tile_cols);
+            ctx->prof_end();
+            ctx->launches += 1;
+            NSP_CUDA_TRY(ctx, cudaGetLastError());
         }
         if (bm_bin > 8 && rows_in(sp, 8, imin(9, bm_bin - 1)) > 0) {
             const int hi = imin(9, bm_bin - 1);
             const int tmax = 32768;
             const int grid = imin(rows_in(sp, 8, hi), sms);
-            if (launch_sym_hash<1024, 1024>(ctx, lanes_for(ctx, sp, 8, hi), grid, (size_t)tmax * 4, a_rpt, a_col,
-                                            b_rpt, b_col, 8, hi, 3, tmax) != 0)
+            if (launch_sym_hash<1024, 1024>(ctx, "sym_hash_cta1024", grid, (size_t)tmax * 4, a_rpt, a_col, b_rpt,
+                                            b_col, 8, hi, 3, tmax) != 0)
                 return -1;
         }
         if (bm_bin > 5 && rows_in(sp, 5, imin(7, bm_bin - 1)) > 0) {
             const int hi = imin(7, bm_bin - 1);
             const int tmax = 8192;
             const int grid = imin(rows_in(sp, 5, hi), (long long)sms * 6);
-            if (launch_sym_hash<256, 256>(ctx, lanes_for(ctx, sp, 5, hi), grid, (size_t)tmax * 4, a_rpt, a_col,
-                                          b_rpt, b_col, 5, hi, 2, tmax) != 0)
+            if (launch_sym_hash<256, 256>(ctx, "sym_hash_cta256", grid, (size_t)tmax * 4, a_rpt, a_col, b_rpt,
+                                          b_col, 5, hi, 2, tmax) != 0)
                 return -1;
         }
         if (rows_in(sp, 1, imin(4, bm_bin - 1)) > 0) {
             const int hi = imin(4, bm_bin - 1);
             const int tmax = 1024;
             const int grid = imin((rows_in(sp, 1, hi) + 7) / 8, (long long)sms * 6);
-            if (launch_sym_hash<32, 256>(ctx, lanes_for(ctx, sp, 1, hi), grid, (size_t)tmax * 4 * 8, a_rpt, a_col,
-                                         b_rpt, b_col, 1, hi, 1, tmax) != 0)
+            if (launch_sym_hash<32, 256>(ctx, "sym_hash_warp", grid, (size_t)tmax * 4 * 8, a_rpt, a_col, b_rpt,
+                                         b_col, 1, hi, 1, tmax) != 0)
                 return -1;
         }
         if (rows_in(sp, 0, 0) > 0) {
             const int grid = imin((rows_in(sp, 0, 0) + 63) / 64, (long long)sms * 8);
+            prof_class(ctx, "sym_pwarp", 0, 0);
             sym_pwarp_kernel<<<grid, 256, 0, ctx->stream>>>(a_rpt, a_col, b_rpt, b_col, sp.d_row_perm,
                                                           sp.d_row_cnt, sp.d_bins);
+            ctx->prof_end();
             ctx->launches += 1;
             NSP_CUDA_TRY(ctx, cudaGetLastError());
         }
