@@ -51,7 +51,8 @@ int nsp_sync(nsp_context *ctx);
 int nsp_set_option(nsp_context *ctx, const char *name, long long value);
 /* With option "profile" = 1 every row-class kernel launch is bracketed by CUDA events on the
  * context's stream.  nsp_profile_dump syncs, writes one line per launch
- * ("<kernel> <ms> <rows> <intermediate products> <A entries>\n") into buf and clears the log. */
+ * ("<kernel> <ms> <rows> <intermediate products> <A entries> <C entries>\n") into buf and clears
+ * the log (<C entries> is 0 for the symbolic kernels). */
 int nsp_profile_dump(nsp_context *ctx, char *buf, size_t buflen);
 /* number of kernels this library launched on the context since creation (bench.py: gpu_launches) */
 long long nsp_launch_count(nsp_context *ctx);

@@ -47,13 +47,14 @@ class Context:
         self.set_option("profile", 1 if on else 0)
 
     def profile_dump(self):
-        """[(kernel, ms, rows, intermediate products, A entries)] of the launches since the last dump."""
+        """[(kernel, ms, rows, intermediate products, A entries, C entries)] of the launches since the
+        last dump (C entries is 0 for the symbolic kernels)."""
         buf = C.create_string_buffer(1 << 16)
         self.check(self.lib.nsp_profile_dump(self.handle, buf, len(buf)))
         out = []
         for line in buf.value.decode().splitlines():
-            n, ms, rows, ip, alen = line.split()
-            out.append((n, float(ms), int(rows), int(ip), int(alen)))
+            n, ms, rows, ip, alen, nout = line.split()
+            out.append((n, float(ms), int(rows), int(ip), int(alen), int(nout)))
         return out
 
     def close(self):

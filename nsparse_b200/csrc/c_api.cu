@@ -59,7 +59,7 @@ int nsp_profile_dump(nsp_context *ctx, char *buf, size_t buflen)
         float ms = 0.f;
         cudaEventElapsedTime(&ms, r.e0, r.e1);
         char line[256];
-        snprintf(line, sizeof(line), "%s %.6f %lld %lld %lld\n", r.name.c_str(), ms, r.rows, r.ip, r.alen);
+        snprintf(line, sizeof(line), "%s %.6f %lld %lld %lld %lld\n", r.name.c_str(), ms, r.rows, r.ip, r.alen, r.out);
         out += line;
         cudaEventDestroy(r.e0);
         cudaEventDestroy(r.e1);

@@ -12,7 +12,7 @@
 struct nsp_spgemm_state {
     int M = 0, K = 0, N = 0;
     int *d_row_cnt = nullptr;     // [M+1] nnz(C_i) after the symbolic phase
-    int *d_row_ip = nullptr;      // [M+1] min(intermediate products of row i, N)
+    int *d_row_ip = nullptr;      // [M+1] intermediate products of row i (saturated at INT_MAX)
     int *d_row_perm = nullptr;    // [M]   rows grouped by bin, heaviest bin first
     int *d_bins = nullptr;        // see spgemm_plan.h for the layout
     unsigned long long *d_binsum = nullptr;
@@ -44,7 +44,7 @@ struct nsp_host_result {
 struct nsp_prof_rec {
     std::string name;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    long long rows = 0, ip = 0, alen = 0;
+    long long rows = 0, ip = 0, alen = 0, out = 0;
 };
 
 struct nsp_context {
@@ -73,7 +73,7 @@ struct nsp_context {
     // per-launch CUDA-event timing of the row-class kernels (nsp_set_option("profile", 1))
     bool profile = false;
     std::vector<nsp_prof_rec> prof;
-    void prof_begin(const char *name, long long rows, long long ip, long long alen)
+    void prof_begin(const char *name, long long rows, long long ip, long long alen, long long out = 0)
     {
         if (!profile) return;
         nsp_prof_rec r;
@@ -81,6 +81,7 @@ struct nsp_context {
         r.rows = rows;
         r.ip = ip;
         r.alen = alen;
+        r.out = out;
         cudaEventCreate(&r.e0);
         cudaEventCreate(&r.e1);
         cudaEventRecord(r.e0, stream);

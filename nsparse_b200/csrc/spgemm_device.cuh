@@ -199,6 +199,7 @@ __device__ __forceinline__ void bitonic_sort_slots(int *keys, real *vals, int n,
 // table size for a row that holds at most `cnt` distinct keys: next pow2 of 4/3*cnt, >= 32
 __device__ __forceinline__ int table_size_for(int cnt, int tmax)
 {
+    if (cnt > tmax) cnt = tmax;
     int want = cnt + cnt / 3 + 1;
     if (want < 32) want = 32;
     int ts = 1 << (32 - __clz(want - 1));

@@ -259,13 +259,14 @@ static inline int num_imin(long long a, long long b) { return (int)(a < b ? a : 
 static inline void num_prof_class(nsp_context *ctx, const char *name, int bin_lo, int bin_hi)
 {
     if (!ctx->profile) return;
-    long long rows = 0, ip = 0, len = 0;
+    long long rows = 0, ip = 0, len = 0, out = 0;
     for (int b = bin_lo; b <= bin_hi; ++b) {
         rows += ctx->sp.h_bins[kBinHist + b];
         ip += (long long)ctx->sp.h_binsum[kSumIp + b];
         len += (long long)ctx->sp.h_binsum[kSumLen + b];
+        out += (long long)ctx->sp.h_binsum[kSumCnt + b];
     }
-    ctx->prof_begin(name, rows, ip, len);
+    ctx->prof_begin(name, rows, ip, len, out);
 }
 
 #define NSP_NUM_ARGS                                                                               \

@@ -73,8 +73,9 @@ count_ip_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
         if (lane == src) ip = s;
     }
     if (row < M) {
+        // row_ip keeps the true product count (saturated); bins and table sizes use min(ip, cap)
+        row_ip[row] = (int)(ip < 0x7fffffffll ? ip : 0x7fffffffll);
         const int v = (int)(ip < (long long)cap ? ip : (long long)cap);
-        row_ip[row] = v;
         const int b = log_bin(v, shift);
         atomicAdd(&s_hist[b], 1);
         if (binsum && len > 0) {
@@ -101,11 +102,12 @@ hist_kernel(const int *__restrict__ values, const int *__restrict__ row_ip,
             unsigned long long *__restrict__ binsum)
 {
     __shared__ int s_hist[kNumBins];
-    __shared__ unsigned long long s_ipsum[kNumBins], s_lensum[kNumBins];
+    __shared__ unsigned long long s_ipsum[kNumBins], s_lensum[kNumBins], s_cntsum[kNumBins];
     if (threadIdx.x < kNumBins) {
         s_hist[threadIdx.x] = 0;
         s_ipsum[threadIdx.x] = 0ull;
         s_lensum[threadIdx.x] = 0ull;
+        s_cntsum[threadIdx.x] = 0ull;
     }
     __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M;
@@ -116,6 +118,7 @@ hist_kernel(const int *__restrict__ values, const int *__restrict__ row_ip,
         if (len > 0) {
             atomicAdd(&s_ipsum[b], (unsigned long long)row_ip[i]);
             atomicAdd(&s_lensum[b], (unsigned long long)len);
+            atomicAdd(&s_cntsum[b], (unsigned long long)values[i]);
         }
     }
     __syncthreads();
@@ -123,6 +126,7 @@ hist_kernel(const int *__restrict__ values, const int *__restrict__ row_ip,
         atomicAdd(&hist[threadIdx.x], s_hist[threadIdx.x]);
         atomicAdd(&binsum[kSumIp + threadIdx.x], s_ipsum[threadIdx.x]);
         atomicAdd(&binsum[kSumLen + threadIdx.x], s_lensum[threadIdx.x]);
+        atomicAdd(&binsum[kSumCnt + threadIdx.x], s_cntsum[threadIdx.x]);
     }
 }
 
@@ -141,7 +145,7 @@ __global__ void bin_offsets_kernel(int *bins)
 }
 
 __global__ void __launch_bounds__(256)
-scatter_rows_kernel(const int *__restrict__ values, int M, int shift, int *__restrict__ bins,
+scatter_rows_kernel(const int *__restrict__ values, int M, int cap, int shift, int *__restrict__ bins,
                     int *__restrict__ row_perm)
 {
     __shared__ int s_cnt[kNumBins];
@@ -151,7 +155,7 @@ scatter_rows_kernel(const int *__restrict__ values, int M, int shift, int *__res
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int b = 0, local = 0;
     if (row < M) {
-        b = log_bin(values[row], shift);
+        b = log_bin(min(values[row], cap), shift);
         local = atomicAdd(&s_cnt[b], 1);
     }
     __syncthreads();
@@ -320,7 +324,7 @@ int plan_by_intprod(nsp_context *ctx, int M, int cap, const int *a_rpt, const in
                                               sp.d_bins + kBinHist, sp.d_binsum,
                                               (unsigned long long *)(sp.d_scalars + kScalarIp));
         bin_offsets_kernel<<<1, 32, 0, st>>>(sp.d_bins);
-        scatter_rows_kernel<<<grid, 256, 0, st>>>(sp.d_row_ip, M, kSymShift, sp.d_bins, sp.d_row_perm);
+        scatter_rows_kernel<<<grid, 256, 0, st>>>(sp.d_row_ip, M, cap, kSymShift, sp.d_bins, sp.d_row_perm);
         ctx->launches += 3;
     }
     NSP_CUDA_TRY(ctx, cudaGetLastError());
@@ -339,7 +343,7 @@ int plan_by_count(nsp_context *ctx, int M, int shift, const int *a_rpt)
         hist_kernel<<<hgrid, 256, 0, st>>>(sp.d_row_cnt, sp.d_row_ip, a_rpt, M, shift,
                                           sp.d_bins + kBinHist, sp.d_binsum);
         bin_offsets_kernel<<<1, 32, 0, st>>>(sp.d_bins);
-        scatter_rows_kernel<<<grid, 256, 0, st>>>(sp.d_row_cnt, M, shift, sp.d_bins, sp.d_row_perm);
+        scatter_rows_kernel<<<grid, 256, 0, st>>>(sp.d_row_cnt, M, 0x7fffffff, shift, sp.d_bins, sp.d_row_perm);
         ctx->launches += 3;
     }
     NSP_CUDA_TRY(ctx, cudaGetLastError());

@@ -18,7 +18,8 @@ constexpr int kBinInts = 128;
 // d_binsum layout (unsigned long long): per-bin sums used to pick lanes-per-B-row
 constexpr int kSumIp = 0;        // [kNumBins] intermediate products of the rows in the bin
 constexpr int kSumLen = 32;      // [kNumBins] A entries of the rows in the bin
-constexpr int kSumInts = 64;
+constexpr int kSumCnt = 64;      // [kNumBins] nnz(C_i) of the rows in the bin (numeric plan only)
+constexpr int kSumInts = 96;
 
 // d_scalars layout (long long)
 constexpr int kScalarIp = 0;     // total intermediate products (uncapped)

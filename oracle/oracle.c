@@ -201,19 +201,31 @@ static size_t pow2_at_least(long long v)
  * the count does not depend on the table size.  rows [row_begin,row_end) only; c_rpt has
  * row_end-row_begin+1 entries and starts at 0.
  * ------------------------------------------------------------------------------------------ */
+long long orc_spgemm_symbolic_n(int row_begin, int row_end, const int *a_rpt, const int *a_col, const int *b_rpt,
+                                const int *b_col, long long *c_rpt, int n_cols);
+
 long long orc_spgemm_symbolic(int row_begin, int row_end, const int *a_rpt, const int *a_col, const int *b_rpt,
                               const int *b_col, long long *c_rpt)
+{
+    return orc_spgemm_symbolic_n(row_begin, row_end, a_rpt, a_col, b_rpt, b_col, c_rpt, 0);
+}
+
+/* n_cols > 0: a row cannot hold more than n_cols distinct keys, so the table is sized from
+ * min(products, n_cols) (keeps the heavy R-MAT rows' tables cache-sized; same counts). */
+long long orc_spgemm_symbolic_n(int row_begin, int row_end, const int *a_rpt, const int *a_col, const int *b_rpt,
+                                const int *b_col, long long *c_rpt, int n_cols)
 {
     const int nrows = row_end - row_begin;
 #pragma omp parallel
     {
         int *tab = NULL;
         size_t cap = 0;
-#pragma omp for schedule(dynamic, 64)
+#pragma omp for schedule(dynamic, 1)
         for (int ii = 0; ii < nrows; ii++) {
             const int i = row_begin + ii;
             long long ip = 0;
             for (int j = a_rpt[i]; j < a_rpt[i + 1]; j++) ip += b_rpt[a_col[j] + 1] - b_rpt[a_col[j]];
+            if (n_cols > 0 && ip > n_cols) ip = n_cols;
             const size_t size = pow2_at_least(2 * ip);
             if (size > cap) {
                 free(tab);
@@ -279,7 +291,7 @@ static int orc_pair_cmp(const void *a, const void *b)
             REAL *racc = NULL;                                                                          \
             orc_pair *out = NULL;                                                                       \
             size_t cap = 0, ocap = 0;                                                                   \
-            _Pragma("omp for schedule(dynamic, 64)")                                                    \
+            _Pragma("omp for schedule(dynamic, 1)")                                                    \
             for (int ii = 0; ii < nrows; ii++) {                                                        \
                 const int i = row_begin + ii;                                                           \
                 const long long nnz = c_rpt[ii + 1] - c_rpt[ii];                                        \

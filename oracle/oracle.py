@@ -40,6 +40,7 @@ def lib():
         L = C.CDLL(path)
         L.orc_spgemm_flop.restype = C.c_longlong
         L.orc_spgemm_symbolic.restype = C.c_longlong
+        L.orc_spgemm_symbolic_n.restype = C.c_longlong
         L.orc_num_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -94,24 +95,26 @@ def spgemm_intprod(a_rpt, a_col, b_rpt):
     return ip
 
 
-def spgemm_symbolic(a_rpt, a_col, b_rpt, b_col, rows=None):
-    """Exact row pointer (int64) of C = A*B for rows [rows[0], rows[1])."""
+def spgemm_symbolic(a_rpt, a_col, b_rpt, b_col, rows=None, n_cols=0):
+    """Exact row pointer (int64) of C = A*B for rows [rows[0], rows[1]).  n_cols (columns of B), when
+    given, only bounds the per-row table size."""
     a_rpt, a_col = _c(a_rpt, np.int32), _c(a_col, np.int32)
     b_rpt, b_col = _c(b_rpt, np.int32), _c(b_col, np.int32)
     r0, r1 = (0, len(a_rpt) - 1) if rows is None else rows
     c_rpt = np.zeros(r1 - r0 + 1, dtype=np.int64)
-    lib().orc_spgemm_symbolic(C.c_int(r0), C.c_int(r1), _p(a_rpt), _p(a_col), _p(b_rpt), _p(b_col), _p(c_rpt))
+    lib().orc_spgemm_symbolic_n(C.c_int(r0), C.c_int(r1), _p(a_rpt), _p(a_col), _p(b_rpt), _p(b_col), _p(c_rpt),
+                                C.c_int(int(n_cols)))
     return c_rpt
 
 
-def spgemm(a_rpt, a_col, a_val, b_rpt, b_col, b_val, rows=None, acc_double=True):
+def spgemm(a_rpt, a_col, a_val, b_rpt, b_col, b_val, rows=None, acc_double=True, n_cols=0):
     """C = A*B (rows [r0,r1) of A): returns (c_rpt int64, c_col int32, c_val dtype of a_val)."""
     dt = np.dtype(a_val.dtype)
     assert dt in (np.dtype(np.float32), np.dtype(np.float64))
     a_rpt, a_col, a_val = _c(a_rpt, np.int32), _c(a_col, np.int32), _c(a_val, dt)
     b_rpt, b_col, b_val = _c(b_rpt, np.int32), _c(b_col, np.int32), _c(b_val, dt)
     r0, r1 = (0, len(a_rpt) - 1) if rows is None else rows
-    c_rpt = spgemm_symbolic(a_rpt, a_col, b_rpt, b_col, (r0, r1))
+    c_rpt = spgemm_symbolic(a_rpt, a_col, b_rpt, b_col, (r0, r1), n_cols)
     nnz = int(c_rpt[-1])
     c_col = np.empty(max(nnz, 1), dtype=np.int32)
     c_val = np.empty(max(nnz, 1), dtype=dt)

@@ -47,7 +47,7 @@ def main():
         print(f"step {step}: symbolic {ts:.2f} ms numeric {tn:.2f} ms total {ts + tn:.2f} ms  "
               f"IP={ip} nnzC={nnz}  GFLOPS={2 * ip / (ts + tn) / 1e6:.1f}", flush=True)
         if step == args.steps - 1:
-            for n, ms, rows, kip, alen in prof:
+            for n, ms, rows, kip, alen, _ in prof:
                 print(f"   {n:20s} {ms:10.3f} ms rows={rows:9d} ip={kip:13d} alen={alen:11d} "
                       f"avgB={kip / max(alen, 1):8.1f}  Gprod/s={kip / max(ms, 1e-9) / 1e6:8.2f}")
         del d_col, d_val, d_rpt64
