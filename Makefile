@@ -11,7 +11,7 @@ OBJ       := build/obj
 LIBDIR    := nsparse_b200/lib
 BIN       := bin
 
-CORE_CU   := context spgemm_plan spgemm_symbolic spgemm_numeric_s spgemm_numeric_d c_api
+CORE_CU   := context spgemm_plan spgemm_symbolic spgemm_numeric_s spgemm_numeric_d c_api amb_convert amb_spmv amb_api
 CORE_OBJ  := $(addprefix $(OBJ)/,$(addsuffix .o,$(CORE_CU))) $(OBJ)/gen.o
 
 .PHONY: all lib compat drivers clean oracle

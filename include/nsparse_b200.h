@@ -159,6 +159,10 @@ int nsp_spmv_amb_d(nsp_context *ctx, const nsp_amb *mat, const double *d_x, doub
 int nsp_spmv_amb_host_s(nsp_context *ctx, const nsp_amb *mat, const float *h_x, float *h_y);
 int nsp_spmv_amb_host_d(nsp_context *ctx, const nsp_amb *mat, const double *h_x, double *h_y);
 
+/* plain device -> host copy on the context's stream (synchronous); lets a binding read the
+ * cudaMalloc'ed arrays of nsp_amb back without a CUDA runtime binding of its own */
+int nsp_memcpy_d2h(nsp_context *ctx, void *h_dst, const void *d_src, size_t bytes);
+
 /* ------------------------------------------------------------------------------------
  * synthetic inputs (host side, OpenMP; counter-based so every rank and the numpy mirror
  * in nsparse_b200/gen.py produce identical edges)

@@ -9,4 +9,5 @@ from .context import Context, default_context          # noqa: F401
 from .csr import CSR, DeviceCSR64                        # noqa: F401
 from .spgemm import (get_spgemm_flop, spgemm_kernel_hash, spgemm_numeric,   # noqa: F401
                      spgemm_symbolic)
+from .amb import AMB, Plan, csr2amb, spmv_amb             # noqa: F401
 from ._lib import NsparseError, load as load_library     # noqa: F401

@@ -63,13 +63,13 @@ SIGNATURES = {
     "nsp_spmv_amb_d": (C.c_int, [vp, C.POINTER(nsp_amb), vp, vp]),
     "nsp_spmv_amb_host_s": (C.c_int, [vp, C.POINTER(nsp_amb), vp, vp]),
     "nsp_spmv_amb_host_d": (C.c_int, [vp, C.POINTER(nsp_amb), vp, vp]),
+    "nsp_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "nsp_gen_rmat_edges": (C.c_int, [C.c_int, ll, C.c_ulonglong, vp, vp]),
 }
 
 
 # symbols declared in the header whose implementation has not landed yet (must be empty at release)
-_PENDING = {"nsp_csr2amb_s", "nsp_csr2amb_d", "nsp_amb_free", "nsp_spmv_amb_s", "nsp_spmv_amb_d",
-            "nsp_spmv_amb_host_s", "nsp_spmv_amb_host_d"}
+_PENDING = set()
 
 
 def load():
