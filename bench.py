@@ -118,30 +118,6 @@ def make_rmat(scale, ef, dtype):
     return gen.rmat_csr(scale, ef, seed=12345, dtype=dtype)
 
 
-def partition_rows_by_ip(a_rpt, a_col, b_rpt, nparts):
-    """Contiguous row blocks of A with ~equal intermediate products."""
-    blen = np.diff(b_rpt).astype(np.int64)
-    per_entry = blen[a_col]
-    cs = np.concatenate([[0], np.cumsum(per_entry)])
-    row_ip_prefix = cs[a_rpt]                       # prefix of IP at row starts, length M+1
-    total = int(row_ip_prefix[-1])
-    cuts = [0]
-    for p in range(1, nparts):
-        cuts.append(int(np.searchsorted(row_ip_prefix, total * p // nparts, side="left")))
-    cuts.append(len(a_rpt) - 1)
-    for i in range(1, len(cuts)):
-        cuts[i] = max(cuts[i], cuts[i - 1])
-    return cuts, total
-
-
-def row_block(a, r0, r1):
-    from nsparse_b200 import CSR
-
-    lo, hi = int(a.rpt[r0]), int(a.rpt[r1])
-    return CSR(r1 - r0, a.N, (a.rpt[r0:r1 + 1] - a.rpt[r0]).astype(np.int32), a.col[lo:hi], a.val[lo:hi],
-               f"{a.matrix_name}[{r0}:{r1}]")
-
-
 def strided_rows(a, stride, offset=0):
     from nsparse_b200 import CSR
 
@@ -253,9 +229,9 @@ def run_ours(args):
 
     t0 = time.time()
     a = make_rmat(args.scale, args.ef, dtype)
-    cuts, total_ip = partition_rows_by_ip(a.rpt, a.col, a.rpt, world)
+    cuts, total_ip = ns.partition_rows_by_ip(a.rpt, a.col, a.rpt, world)
     r0, r1 = cuts[rank], cuts[rank + 1]
-    a_loc = a if world == 1 else row_block(a, r0, r1)
+    a_loc = a if world == 1 else ns.row_block(a, r0, r1)
     gen_s = time.time() - t0
 
     ctx = ns.Context(local)
@@ -274,29 +250,12 @@ def run_ours(args):
     state = {}
 
     def step():
-        c = ns.spgemm_kernel_hash(a_loc, a, ctx)
         if world > 1:
-            c = allgatherv_c(c)
+            c = ns.spgemm_kernel_hash_mgpu(a_loc, a, cuts, a.M, total_ip, ctx)
+        else:
+            c = ns.spgemm_kernel_hash(a_loc, a, ctx)
         state["c"] = c
         return c
-
-    def allgatherv_c(c):
-        # sizes -> displacements -> grouped broadcasts into the final buffers (NCCL has no native
-        # v-collective; torch's all_gather with uneven outputs issues exactly that group)
-        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
-        mine = torch.tensor([c.nnz], dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(sizes, mine)
-        sz = sizes.tolist()
-        disp = np.concatenate([[0], np.cumsum(sz)]).astype(np.int64)
-        tot = int(disp[-1])
-        full_col = torch.empty(max(tot, 1), dtype=torch.int32, device=dev)
-        full_val = torch.empty(max(tot, 1), dtype=tdt, device=dev)
-        full_rpt = torch.empty(a.M + 1, dtype=torch.int64, device=dev)
-        dist.all_gather([full_col[disp[i]:disp[i + 1]] for i in range(world)], c.d_col[:c.nnz])
-        dist.all_gather([full_val[disp[i]:disp[i + 1]] for i in range(world)], c.d_val[:c.nnz])
-        dist.all_gather([full_rpt[cuts[i]:cuts[i + 1]] for i in range(world)], c.d_rpt64[:-1] + int(disp[rank]))
-        full_rpt[-1] = tot
-        return ns.DeviceCSR64(a.M, a.N, full_rpt, full_col, full_val, tot, total_ip)
 
     for _ in range(args.warmup):
         step()

@@ -1,0 +1,95 @@
+"""Host logic of the multi-GPU SpGEMM on CPU: world_size-2 gloo processes, each computing its row block
+with the CPU oracle and gathering through nsparse_b200.multi_gpu.allgatherv_csr.  (The GPU kernels are
+not involved: this covers partitioning, displacements and the row-pointer rebasing.)"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _mat(seed=0, m=300, n=300, dens=0.03):
+    rng = np.random.default_rng(seed)
+    a = sp.random(m, n, density=dens, random_state=rng, format="csr")
+    a.data = rng.integers(1, 5, a.nnz).astype(np.float64)
+    a.sort_indices()
+    # make the load very uneven so the cuts are not the trivial halves
+    a = sp.vstack([a[:10].toarray().repeat(1, axis=0) * 0 + 1, a[10:]]).tocsr()
+    a.sort_indices()
+    return a
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    from nsparse_b200 import multi_gpu as mg
+    from nsparse_b200.csr import CSR
+    from oracle import oracle
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a = _mat()
+    A = CSR.from_scipy(a, np.float64)
+    cuts, total = mg.partition_rows_by_ip(A.rpt, A.col, A.rpt, world)
+    blk = mg.row_block(A, cuts[rank], cuts[rank + 1])
+    rpt, col, val = oracle.spgemm(blk.rpt, blk.col, blk.val, A.rpt, A.col, A.val)
+    out = mg.allgatherv_csr(torch.from_numpy(rpt), torch.from_numpy(col), torch.from_numpy(val), int(rpt[-1]),
+                            cuts, A.M)
+    full = oracle.spgemm(A.rpt, A.col, A.val, A.rpt, A.col, A.val)
+    ok = (np.array_equal(out[0].numpy(), full[0]) and np.array_equal(out[1].numpy()[:out[3]], full[1])
+          and np.array_equal(out[2].numpy()[:out[3]], full[2]) and out[3] == int(full[0][-1]))
+    q.put((rank, ok, cuts, total))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_block_allgatherv_gloo(world):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _, _ in res), res
+    cuts = res[0][2]
+    assert cuts[0] == 0 and cuts[-1] == 300 and all(c0 <= c1 for c0, c1 in zip(cuts, cuts[1:]))
+
+
+def test_partition_balances_intermediate_products():
+    sys.path.insert(0, ROOT)
+    from nsparse_b200 import multi_gpu as mg
+    from oracle import oracle
+
+    a = _mat(3, 2000, 2000, 0.01)
+    ip = oracle.spgemm_intprod(a.indptr.astype(np.int32), a.indices.astype(np.int32), a.indptr.astype(np.int32))
+    for parts in (1, 2, 4, 8):
+        cuts, total = mg.partition_rows_by_ip(a.indptr, a.indices, a.indptr, parts)
+        assert total == int(ip.sum()) and len(cuts) == parts + 1
+        loads = [int(ip[cuts[i]:cuts[i + 1]].sum()) for i in range(parts)]
+        assert sum(loads) == total
+        assert max(loads) <= total / parts + ip.max()
+    # degenerate: more parts than rows, empty matrix
+    cuts, total = mg.partition_rows_by_ip(np.array([0, 1, 2]), np.array([0, 1]), np.array([0, 1, 2]), 4)
+    assert cuts[0] == 0 and cuts[-1] == 2 and total == 2
+    cuts, total = mg.partition_rows_by_ip(np.zeros(4, np.int64), np.zeros(0, np.int64), np.zeros(4, np.int64), 2)
+    assert cuts == [0, 0, 3] and total == 0
