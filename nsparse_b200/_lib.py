@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnsparse_b200.so")
+LIB_PATH = os.environ.get("NSP_LIB_PATH") or os.path.join(_HERE, "lib", "libnsparse_b200.so")
 
 _lib = None
 

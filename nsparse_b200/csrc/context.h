@@ -62,6 +62,7 @@ struct nsp_context {
     // options (nsp_set_option)
     long long opt_sym_bitmap_min = -1;   // rows with min(ip,N) >  this go to the bitmap kernel (-1: default)
     long long opt_num_bitmap_min = -1;   // rows with nnz(C_i)  >  this go to the bitmap-rank kernel
+    long long opt_debug = 0;             // development only: bit 0 skip emit, 1 skip value pass, 2 skip zero-fill
     long long opt_lanes_per_brow = 0;    // 0: pick from nnz(B)/K
 
     nsp_spgemm_state sp;

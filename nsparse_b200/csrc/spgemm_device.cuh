@@ -134,6 +134,119 @@ __device__ __forceinline__ void for_each_product(int t, int a_beg, int a_end,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row traversal for the CTA-per-row kernels of the heavy classes -- WARP-ALIGNED PARTS.
+//
+// The flat traversal above balances perfectly but pays for it per product: every lane tracks its
+// own A entry (compare + divergent advance loop), which made the bitmap kernels issue-bound at
+// 1.6 (symbolic) / 2.4 (numeric, per pass) warp instructions per product with 27 % of the stall
+// samples on barriers (profiles/r1_ncu_full_bitmap_scale18.txt).  Heavy rows of C are unions of
+// LONG B rows (R-MAT scale 20: 1300 entries on average), so here the unit of work is a PART: up to
+// kPartLen consecutive products of ONE B row.  A warp claims parts from a shared-memory counter
+// (dynamic balance at 256-product granularity), finds the part's entry with two ballots, and then
+// all 32 lanes stream the same B row: one coalesced 128-byte load of B.col (and B.val) per 32
+// products, a warp-uniform a_ij, no per-lane bookkeeping.
+// ---------------------------------------------------------------------------------------------
+#ifndef NSP_PART_LEN
+#define NSP_PART_LEN 256
+#endif
+constexpr int kPartLen = NSP_PART_LEN;
+
+template <int BS, typename real>
+struct PartScratch {
+    int pre[BS + 1];   // exclusive prefix of the parts of the slab's entries
+    int kb[BS];        // first product of the entry in B.col / B.val
+    int len[BS];       // products of the entry
+    real av[BS];       // a_ij (numeric only)
+    int wtot[BS / 32 + 1];
+    int next;          // next unclaimed part
+};
+
+// Stage the slab [base, base + BS) of the A row: B-row starts / lengths / a_ij and the part prefix.
+// Ends with a barrier; returns the number of parts.
+template <int BS, bool kLoadVal, typename real>
+__device__ __forceinline__ int stage_parts(int t, int base, int a_end, const int *__restrict__ a_col,
+                                           const real *__restrict__ a_val, const int *__restrict__ b_rpt,
+                                           PartScratch<BS, real> &s)
+{
+    int len = 0, kb = 0;
+    if (base + t < a_end) {
+        const int ac = ld_stream(a_col + base + t);
+        kb = ld_nc(b_rpt + ac);
+        len = ld_nc(b_rpt + ac + 1) - kb;
+        if (kLoadVal) s.av[t] = ld_stream(a_val + base + t);
+    }
+    s.kb[t] = kb;
+    s.len[t] = len;
+    const int inc = group_inclusive_scan<BS>((len + kPartLen - 1) / kPartLen, t, s.wtot);
+    s.pre[t + 1] = inc;
+    if (t == 0) s.pre[0] = 0;
+    __syncthreads();
+    return s.pre[BS];
+}
+
+// Walk the staged slab's parts.  The caller guarantees a barrier between stage_parts (or the
+// previous run_parts) and this call, and s.next == BS / 32 on entry; ends with a barrier that
+// also re-arms s.next.
+template <int BS, bool kNumeric, typename real, typename F>
+__device__ __forceinline__ void run_parts(int t, int total, const int *__restrict__ b_col,
+                                          const real *__restrict__ b_val, PartScratch<BS, real> &s, F &&f)
+{
+    constexpr int NW = BS / 32;
+    constexpr int S1 = BS / 32;   // level-1 stride of the 32-ary entry search
+    const int lane = t & 31;
+    int q = t >> 5;
+    while (q < total) {
+        // entry of part q = largest e with pre[e] <= q
+        const unsigned q1 = __ballot_sync(0xffffffffu, s.pre[lane * S1] <= q);
+        int e = (__popc(q1) - 1) * S1;
+        if (S1 > 1) {
+            const unsigned q2 = __ballot_sync(0xffffffffu, lane < S1 && s.pre[e + lane] <= q);
+            e += __popc(q2) - 1;
+        }
+        const int k0 = s.kb[e] + (q - s.pre[e]) * kPartLen;
+        const int k1 = min(s.kb[e] + s.len[e], k0 + kPartLen);
+        const real av = kNumeric ? s.av[e] : real(0);
+#pragma unroll 1
+        for (int k = k0 + lane; k < k1; k += 128) {
+            int c[4];
+            real v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int kk = k + 32 * u;
+                c[u] = -1;
+                if (kk < k1) {
+                    c[u] = ld_nc(b_col + kk);
+                    if (kNumeric) v[u] = av * ld_nc(b_val + kk);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (c[u] >= 0) f(c[u], kNumeric ? v[u] : real(0));
+        }
+        if (lane == 0) q = atomicAdd(&s.next, 1);
+        q = __shfl_sync(0xffffffffu, q, 0);
+    }
+    __syncthreads();
+    if (t == 0) s.next = NW;
+}
+
+template <int BS, bool kNumeric, typename real, typename F>
+__device__ __forceinline__ void for_each_product_parts(int t, int a_beg, int a_end,
+                                                       const int *__restrict__ a_col,
+                                                       const real *__restrict__ a_val,
+                                                       const int *__restrict__ b_rpt,
+                                                       const int *__restrict__ b_col,
+                                                       const real *__restrict__ b_val,
+                                                       PartScratch<BS, real> &s, F &&f)
+{
+    for (int base = a_beg; base < a_end; base += BS) {
+        if (t == 0) s.next = BS / 32;      // ordered before the claims by stage_parts' barriers
+        const int total = stage_parts<BS, kNumeric, real>(t, base, a_end, a_col, a_val, b_rpt, s);
+        run_parts<BS, kNumeric, real>(t, total, b_col, b_val, s, f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Open-addressing insert, linear probing, key-only (symbolic).  Returns 1 if the key was new.
 // Same scheme as the reference probe loop (kernel_spgemm_hash_d.cu:299-317) but the table is
 // sized per row (mask) and never runs above 3/4 load.

@@ -137,25 +137,28 @@ num_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
 }
 
 // ---- bitmap + rank class ------------------------------------------------------------------------
-// shared memory: bm[nw] 64-bit bitmap words of the column tile, pre[nw] exclusive popcount prefix
-template <typename real, int BS>
+// shared memory: bm[nw] 64-bit bitmap words of the column tile, pre[nw] exclusive popcount prefix.
+// Every warp owns a contiguous segment of the words (lanes interleaved, so the 8-byte reads are
+// bank-conflict free): the prefix needs two barriers per tile whatever N is, and a lane emits the
+// columns of its words as one contiguous run of C.col.
+template <typename real, int BS, bool kSingle>
 __global__ void __launch_bounds__(BS, 1)
 num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                   const real *__restrict__ a_val, const int *__restrict__ b_rpt,
                   const int *__restrict__ b_col, const real *__restrict__ b_val,
                   const long long *__restrict__ c_rpt, int *__restrict__ c_col, real *__restrict__ c_val,
                   const int *__restrict__ row_perm, int *__restrict__ bins, int bin_lo, int bin_hi,
-                  int queue, int N, int tile_cols)
+                  int queue, int N, int tile_cols, int dbg)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ FlatScratch<BS, real> s_flat;
+    constexpr int NW = BS / 32;
+    __shared__ PartScratch<BS, real> s_part;
     __shared__ int s_row;
-    __shared__ int s_warp[BS / 32];
-    __shared__ int s_carry;
-    const int tile_words = tile_cols >> 6;
+    __shared__ int s_wsum[NW];
+    const int tile_words = (tile_cols + 63) >> 6;
     unsigned long long *bm = reinterpret_cast<unsigned long long *>(smem_raw);
     unsigned *bm32 = reinterpret_cast<unsigned *>(smem_raw);
-    int *pre = reinterpret_cast<int *>(smem_raw + sizeof(unsigned long long) * (size_t)tile_words);
+    int *pre = reinterpret_cast<int *>(smem_raw + sizeof(unsigned long long) * (size_t)((tile_words + 1) & ~1));
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     int lo, hi;
     class_range(bins, bin_lo, bin_hi, lo, hi);
@@ -171,75 +174,103 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
         for (int t0 = 0; t0 < N; t0 += tile_cols) {
             const int ncols = min(tile_cols, N - t0);
             const int nw = (ncols + 63) >> 6;
-            for (int i = t; i < nw; i += BS) bm[i] = 0ull;
-            if (t == 0) s_carry = 0;
+            {
+                uint4 *bm4 = reinterpret_cast<uint4 *>(bm);
+                const int nw4 = (nw + 1) >> 1;
+                for (int i = t; i < nw4; i += BS) bm4[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
             __syncthreads();
-            // pass 1: structure of the tile
-            for_each_product<BS, false, real>(
-                t, a_beg, a_end, a_col, a_val, b_rpt, b_col, b_val, s_flat, [&](int c, real) {
-                    const unsigned cc = (unsigned)(c - t0);
-                    if (cc < (unsigned)ncols) {
-                        const unsigned bit = 1u << (cc & 31);
-                        if (!(*((volatile unsigned *)(bm32 + (cc >> 5))) & bit))
-                            atomicOr(bm32 + (cc >> 5), bit);
-                    }
-                });
+            // pass 1: structure of the tile.  A row whose A entries fit one slab (nearly all) is
+            // staged once, with its values, and pass 2 walks the same staged parts again.
+            const bool one_slab = a_end - a_beg <= BS;
+            int staged_total = 0;
+            auto mark = [&](int c, real) {
+                const unsigned cc = (unsigned)(c - t0);
+                if (kSingle || cc < (unsigned)ncols) {
+                    const unsigned bit = 1u << (cc & 31);
+                    unsigned *w = bm32 + (cc >> 5);
+                    if (!(*((volatile unsigned *)w) & bit)) atomicOr(w, bit);
+                }
+            };
+            if (one_slab) {
+                if (t == 0) s_part.next = NW;
+                staged_total = stage_parts<BS, true, real>(t, a_beg, a_end, a_col, a_val, b_rpt, s_part);
+                run_parts<BS, false, real>(t, staged_total, b_col, b_val, s_part, mark);
+            } else {
+                for_each_product_parts<BS, false, real>(t, a_beg, a_end, a_col, a_val, b_rpt, b_col, b_val, s_part,
+                                                        mark);
+            }
+            // exclusive prefix of the per-word popcounts: warp totals, then per-warp running scan
+            const int seg = ((nw + BS - 1) / BS) * 32;         // words per warp (multiple of 32)
+            const int w0 = wid * seg, w1 = min(nw, w0 + seg);
+            int tot = 0;
+            for (int j = w0 + lane; j < w1; j += 32) tot += __popcll(bm[j]);
+            tot = warp_sum(tot);
+            if (lane == 0) s_wsum[wid] = tot;
             __syncthreads();
-            // exclusive prefix of the per-word popcounts, BS words at a time
-            for (int base = 0; base < nw; base += BS) {
-                const int w = base + t;
-                const int carry = s_carry;   // written before the barrier that ended the last round
-                const int c = w < nw ? __popcll(bm[w]) : 0;
+            int carry, tile_nnz;
+            {
+                const int ws = lane < NW ? s_wsum[lane] : 0;
+                carry = warp_sum(lane < wid ? ws : 0);
+                tile_nnz = warp_sum(ws);
+            }
+            for (int jb = w0; jb < w1; jb += 32) {
+                const int j = jb + lane;
+                const int c = j < w1 ? __popcll(bm[j]) : 0;
                 int inc = c;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const int v = __shfl_up_sync(0xffffffffu, inc, o);
                     if (lane >= o) inc += v;
                 }
-                if (lane == 31) s_warp[wid] = inc;
-                __syncthreads();
-                if (wid == 0) {
-                    const int wv = lane < BS / 32 ? s_warp[lane] : 0;
-                    int winc = wv;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int v = __shfl_up_sync(0xffffffffu, winc, o);
-                        if (lane >= o) winc += v;
-                    }
-                    if (lane < BS / 32) s_warp[lane] = winc - wv;
-                    if (lane == 31) s_carry = carry + winc;
-                }
-                __syncthreads();
-                if (w < nw) pre[w] = carry + s_warp[wid] + inc - c;
-                __syncthreads();
+                if (j < w1) pre[j] = carry + inc - c;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
             }
-            const int tile_nnz = s_carry;
-            // emit the (sorted) columns of the tile and clear their values
-            for (int w = t; w < nw; w += BS) {
-                unsigned long long bits = bm[w];
-                long long p = out + pre[w];
-                const int cbase = t0 + (w << 6);
-                while (bits) {
-                    const int b = __ffsll((long long)bits) - 1;
-                    bits &= bits - 1;
-                    c_col[p] = cbase + b;
-                    c_val[p] = real(0);
-                    ++p;
+            // values start at zero (coalesced), columns come straight from the bitmap (sorted)
+            if (!(dbg & 4)) for (int i = t; i < tile_nnz; i += BS) c_val[out + i] = real(0);
+            if (!(dbg & 1)) {
+                int *crow = c_col + out;
+                for (int jb = w0; jb < w1; jb += 32) {
+                    const int j = jb + lane;
+                    if (j < w1) {
+                        // 32-bit halves, 32-bit output index: ~9 instructions per emitted column
+                        unsigned lo32 = bm32[2 * j], hi32 = bm32[2 * j + 1];
+                        int idx = pre[j];
+                        const int cbase = t0 + (j << 6);
+                        while (lo32) {
+                            crow[idx++] = cbase + __ffs((int)lo32) - 1;
+                            lo32 &= lo32 - 1;
+                        }
+                        while (hi32) {
+                            crow[idx++] = cbase + 31 + __ffs((int)hi32);
+                            hi32 &= hi32 - 1;
+                        }
+                    }
                 }
             }
             __syncthreads();
             // pass 2: values
-            for_each_product<BS, true, real>(
-                t, a_beg, a_end, a_col, a_val, b_rpt, b_col, b_val, s_flat, [&](int c, real v) {
-                    const unsigned cc = (unsigned)(c - t0);
-                    if (cc < (unsigned)ncols) {
-                        const unsigned w = cc >> 6;
-                        const int rank = pre[w] + __popcll(bm[w] & ((1ull << (cc & 63)) - 1ull));
-                        atomicAdd(c_val + out + rank, v);
-                    }
-                });
+            real *cv = c_val + out;
+            auto add = [&](int c, real v) {
+                const unsigned cc = (unsigned)(c - t0);
+                if (kSingle || cc < (unsigned)ncols) {
+                    // rank = prefix of the 64-bit word + set bits below cc, in 32-bit operations
+                    const unsigned w = cc >> 6;
+                    const uint2 word = *reinterpret_cast<const uint2 *>(bm + w);
+                    const unsigned below = (1u << (cc & 31)) - 1u;
+                    const bool upper = (cc & 32) != 0;
+                    const int rank = pre[w] + __popc(word.x & (upper ? 0xffffffffu : below)) +
+                                     __popc(word.y & (upper ? below : 0u));
+                    atomicAdd(cv + rank, v);
+                }
+            };
+            if (dbg & 2) {
+            } else if (one_slab)
+                run_parts<BS, true, real>(t, staged_total, b_col, b_val, s_part, add);
+            else
+                for_each_product_parts<BS, true, real>(t, a_beg, a_end, a_col, a_val, b_rpt, b_col, b_val, s_part,
+                                                       add);
             out += tile_nnz;
-            __syncthreads();
         }
     }
 }
@@ -307,8 +338,8 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
     //   bins 8..9      <= 8192      CTA(1024) / row, <= 16384 slots (128 KiB fp32 / 192 KiB fp64)
     //   bins >= bm_bin              CTA(1024) / row, bitmap + rank over column tiles
     const int smem_cap = ctx->max_smem_optin - kStaticSmemReserve;
-    const int tile_max = (smem_cap / 12) * 64;
-    const int tile_cols = N < tile_max ? ((N + 63) / 64) * 64 : tile_max;
+    const int tile_max = ((smem_cap - 64) / 24) * 128;
+    const int tile_cols = N < tile_max ? ((N + 127) / 128) * 128 : tile_max;
     const int slot_bytes = 4 + (int)sizeof(real);
     int bm_bin = 10;
     if (N <= tile_max) {
@@ -326,12 +357,13 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
     }
     const int sms = ctx->sm_count;
     if (num_rows_in(sp, bm_bin, kNumBins - 1) > 0) {
-        const size_t smem = (size_t)(tile_cols / 64) * 12;
+        const size_t tw = (size_t)(tile_cols + 63) / 64;
+        const size_t smem = ((tw + 1) & ~size_t(1)) * 8 + tw * 4 + 16;
         const int grid = num_imin(num_rows_in(sp, bm_bin, kNumBins - 1), (long long)sms);
-        auto kern = num_bitmap_kernel<real, 1024>;
+        auto kern = N <= tile_max ? num_bitmap_kernel<real, 1024, true> : num_bitmap_kernel<real, 1024, false>;
         NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         num_prof_class(ctx, "num_bitmap", bm_bin, kNumBins - 1);
-        kern<<<grid, 1024, smem, ctx->stream>>>(NSP_NUM_ARGS, bm_bin, kNumBins - 1, 4, N, tile_cols);
+        kern<<<grid, 1024, smem, ctx->stream>>>(NSP_NUM_ARGS, bm_bin, kNumBins - 1, 4, N, tile_cols, (int)ctx->opt_debug);
         ctx->prof_end();
         ctx->launches += 1;
         NSP_CUDA_TRY(ctx, cudaGetLastError());

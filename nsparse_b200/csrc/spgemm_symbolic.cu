@@ -115,16 +115,19 @@ sym_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
 }
 
 // ---- bitmap class: one CTA per row, one pass over the row's products per column tile -------------
-template <int BS>
+// kSingle: the whole row fits one tile (N <= tile_cols), no column-range test per product.
+// New columns are counted where they are inserted (the old word of the atomicOr says whether the
+// bit was new), so there is no popcount pass over the N/32 words afterwards.
+template <int BS, bool kSingle>
 __global__ void __launch_bounds__(BS, 1)
 sym_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                   const int *__restrict__ b_rpt, const int *__restrict__ b_col,
                   const int *__restrict__ row_perm, int *__restrict__ row_cnt, int *__restrict__ bins,
                   int bin_lo, int bin_hi, int queue, int N, int tile_cols)
 {
-    extern __shared__ int smem_i[];
+    extern __shared__ __align__(16) int smem_i[];
     unsigned *bm = reinterpret_cast<unsigned *>(smem_i);
-    __shared__ FlatScratch<BS, float> s_flat;
+    __shared__ PartScratch<BS, float> s_part;
     __shared__ int s_row, s_cnt;
     const int t = threadIdx.x;
     int lo, hi;
@@ -140,29 +143,28 @@ sym_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
         if (r >= n) break;
         const int rid = row_perm[lo + r];
         const int a_beg = a_rpt[rid], a_end = a_rpt[rid + 1];
+        int cnt = 0;
         for (int t0 = 0; t0 < N; t0 += tile_cols) {
             const int ncols = min(tile_cols, N - t0);
-            const int nw = (ncols + 31) >> 5;
-            for (int i = t; i < nw; i += BS) bm[i] = 0u;
+            const int nw4 = (ncols + 127) >> 7;
+            uint4 *bm4 = reinterpret_cast<uint4 *>(bm);
+            for (int i = t; i < nw4; i += BS) bm4[i] = make_uint4(0u, 0u, 0u, 0u);
             __syncthreads();
-            for_each_product<BS, false, float>(
-                t, a_beg, a_end, a_col, (const float *)nullptr, b_rpt, b_col, (const float *)nullptr, s_flat,
+            for_each_product_parts<BS, false, float>(
+                t, a_beg, a_end, a_col, (const float *)nullptr, b_rpt, b_col, (const float *)nullptr, s_part,
                 [&](int c, float) {
                     const unsigned cc = (unsigned)(c - t0);
-                    if (cc < (unsigned)ncols) {
+                    if (kSingle || cc < (unsigned)ncols) {
                         const unsigned bit = 1u << (cc & 31);
-                        if (!(*((volatile unsigned *)(bm + (cc >> 5))) & bit)) atomicOr(bm + (cc >> 5), bit);
+                        unsigned *w = bm + (cc >> 5);
+                        if (!(*((volatile unsigned *)w) & bit)) cnt += !(atomicOr(w, bit) & bit);
                     }
                 });
-            __syncthreads();
-            int cnt = 0;
-            for (int i = t; i < nw; i += BS) cnt += __popc(bm[i]);
-            cnt = warp_sum(cnt);
-            if ((t & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
-            __syncthreads();
         }
-        if (t == 0) row_cnt[rid] = s_cnt;
+        cnt = warp_sum(cnt);
+        if ((t & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
         __syncthreads();
+        if (t == 0) row_cnt[rid] = s_cnt;
     }
 }
 
@@ -227,8 +229,8 @@ int spgemm_symbolic(nsp_context *ctx, int M, int K, int N, const int *a_rpt, con
     //   bins 8..9      <= 16384     CTA(1024) / row, <= 32768 slots (128 KiB)
     //   bins >= bm_bin              CTA(1024) / row, bitmap over column tiles
     const int smem_cap = ctx->max_smem_optin - kStaticSmemReserve;
-    const int tile_max = (smem_cap / 4) * 32;                      // columns one bitmap tile can hold
-    const int tile_cols = N < tile_max ? ((N + 31) / 32) * 32 : tile_max;
+    const int tile_max = (smem_cap / 16) * 128;                    // columns one bitmap tile can hold
+    const int tile_cols = N < tile_max ? ((N + 127) / 128) * 128 : tile_max;
     int bm_bin = 10;
     if (N <= tile_max) {
         // one tile covers the row: clearing + counting the bitmap costs ~N/8 bytes of shared-memory
@@ -248,9 +250,9 @@ int spgemm_symbolic(nsp_context *ctx, int M, int K, int N, const int *a_rpt, con
     if (M > 0) {
         // heaviest first
         if (rows_in(sp, bm_bin, kNumBins - 1) > 0) {
-            const size_t smem = (size_t)(tile_cols / 32) * 4;
+            const size_t smem = (size_t)((tile_cols + 127) / 128) * 16;
             const int grid = imin(rows_in(sp, bm_bin, kNumBins - 1), (long long)sms);
-            auto kern = sym_bitmap_kernel<1024>;
+            auto kern = N <= tile_max ? sym_bitmap_kernel<1024, true> : sym_bitmap_kernel<1024, false>;
             NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             prof_class(ctx, "sym_bitmap", bm_bin, kNumBins - 1);
             kern<<<grid, 1024, smem, ctx->stream>>>(a_rpt, a_col, b_rpt, b_col, sp.d_row_perm, sp.d_row_cnt,
