@@ -40,6 +40,9 @@ int nsp_set_option(nsp_context *ctx, const char *name, long long value)
     else if (!strcmp(name, "num_bitmap_min")) ctx->opt_num_bitmap_min = value;
     else if (!strcmp(name, "profile")) ctx->profile = value != 0;
     else if (!strcmp(name, "debug")) ctx->opt_debug = value;
+    else if (!strcmp(name, "no_vec")) ctx->opt_no_vec = value;
+    else if (!strcmp(name, "sym_window_shift")) ctx->opt_sym_window_shift = value;
+    else if (!strcmp(name, "num_window_shift")) ctx->opt_num_window_shift = value;
     else if (!strcmp(name, "lanes_per_brow")) {
         if (value != 0 && value != 4 && value != 8 && value != 16 && value != 32)
             return ctx->fail(NSP_ERR_ARG, "lanes_per_brow must be 0, 4, 8, 16 or 32");

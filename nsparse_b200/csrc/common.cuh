@@ -15,7 +15,7 @@ namespace nsp {
 // ---------------------------------------------------------------------------------------------
 constexpr int kWarp = 32;
 constexpr int kMaxSmemOptin = 227 * 1024;   // bytes per CTA on sm_100
-constexpr int kStaticSmemReserve = 24 * 1024;   // static __shared__ of the 1024-thread kernels (row slab)
+constexpr int kStaticSmemReserve = 34 * 1024;   // static __shared__ of the 1024-thread kernels (row slab)
 constexpr int kEmptyKey = -1;              // columns are >= 0, so -1 marks a free slot (ref: init_check)
 constexpr unsigned kHashMul = 107u;         // HASH_SCAL of the reference (kernel_spgemm_hash_d.cu:30);
                                             // applied to the UNSIGNED column so col >= 20,070,414 cannot

@@ -23,6 +23,8 @@ struct nsp_spgemm_state {
     long long *h_scalars = nullptr;   // pinned mirror
     int lanes_per_brow = 32;
     bool symbolic_done = false;
+    long long b_nnz = 0;          // nnz(B) = B.rpt[K], read back by the symbolic plan
+    bool b_sorted = true;         // rows of B column-sorted (checked by the symbolic plan)
 };
 
 struct nsp_host_result {
@@ -62,6 +64,9 @@ struct nsp_context {
     // options (nsp_set_option)
     long long opt_sym_bitmap_min = -1;   // rows with min(ip,N) >  this go to the bitmap kernel (-1: default)
     long long opt_num_bitmap_min = -1;   // rows with nnz(C_i)  >  this go to the bitmap-rank kernel
+    long long opt_sym_window_shift = 0;  // log2 of the symbolic bitmap window (0: default 20)
+    long long opt_num_window_shift = 0;  // log2 of the numeric bitmap window (0: default 19)
+    long long opt_no_vec = 0;            // 1: never read B.col with 128-bit loads (tests)
     long long opt_debug = 0;             // development only: bit 0 skip emit, 1 skip value pass, 2 skip zero-fill
     long long opt_lanes_per_brow = 0;    // 0: pick from nnz(B)/K
 

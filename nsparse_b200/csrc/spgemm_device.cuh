@@ -137,14 +137,13 @@ __device__ __forceinline__ void for_each_product(int t, int a_beg, int a_end,
 // Row traversal for the CTA-per-row kernels of the heavy classes -- WARP-ALIGNED PARTS.
 //
 // The flat traversal above balances perfectly but pays for it per product: every lane tracks its
-// own A entry (compare + divergent advance loop), which made the bitmap kernels issue-bound at
-// 1.6 (symbolic) / 2.4 (numeric, per pass) warp instructions per product with 27 % of the stall
-// samples on barriers (profiles/r1_ncu_full_bitmap_scale18.txt).  Heavy rows of C are unions of
-// LONG B rows (R-MAT scale 20: 1300 entries on average), so here the unit of work is a PART: up to
-// kPartLen consecutive products of ONE B row.  A warp claims parts from a shared-memory counter
-// (dynamic balance at 256-product granularity), finds the part's entry with two ballots, and then
-// all 32 lanes stream the same B row: one coalesced 128-byte load of B.col (and B.val) per 32
-// products, a warp-uniform a_ij, no per-lane bookkeeping.
+// own A entry (compare + divergent advance loop).  Heavy rows of C are unions of LONG B rows (R-MAT
+// scale 20: 1300 entries on average, 95 % of the products come from B rows longer than 256), so here
+// the unit of work is a PART: up to kPartLen consecutive products of ONE B row.  Warp w takes the
+// parts w, w + 32, ... of the staged slab (static round robin: a shared-memory claim counter cost
+// 10 % of the stall samples of the round-1 kernel), finds the part's entry with two ballots, issues
+// ALL loads of the part before the first use (8 x 128 B of B.col, and of B.val, in flight per
+// warp), and then every lane handles its products with a warp-uniform a_ij.
 // ---------------------------------------------------------------------------------------------
 #ifndef NSP_PART_LEN
 #define NSP_PART_LEN 256
@@ -154,15 +153,37 @@ constexpr int kPartLen = NSP_PART_LEN;
 template <int BS, typename real>
 struct PartScratch {
     int pre[BS + 1];   // exclusive prefix of the parts of the slab's entries
-    int kb[BS];        // first product of the entry in B.col / B.val
-    int len[BS];       // products of the entry
+    int pre1[BS / 32]; // pre[32 * i]: bank-conflict-free first level of the entry search
+    int kb[BS];        // first product of the entry's current segment in B.col / B.val
+    int len[BS];       // products of the segment
+    int cur[BS];       // cursor: first product of the entry not yet consumed by the value chunks
+    int end[BS];       // end of the entry's segment in the current column window
     real av[BS];       // a_ij (numeric only)
     int wtot[BS / 32 + 1];
-    int next;          // next unclaimed part
 };
 
+// Parts of a segment [kb, kb + len) of B.col / B.val: consecutive kPartLen-element pieces of the global
+// arrays counted from the 16-byte aligned index kb & ~3, so that the mark pass can read a part with
+// 128-bit loads; elements before kb in the first part are masked off.
+__device__ __forceinline__ int parts_of(int kb, int len)
+{
+    return len > 0 ? ((kb & 3) + len + kPartLen - 1) / kPartLen : 0;
+}
+
+// parts prefix of the staged segments; two barriers; returns the number of parts
+template <int BS, typename real>
+__device__ __forceinline__ int scan_parts(int t, int kb, int len, PartScratch<BS, real> &s)
+{
+    const int np = parts_of(kb, len);
+    const int inc = group_inclusive_scan<BS>(np, t, s.wtot);
+    s.pre[t + 1] = inc;
+    if ((t & 31) == 0) s.pre1[t >> 5] = inc - np;
+    if (t == 0) s.pre[0] = 0;
+    __syncthreads();
+    return s.pre[BS];
+}
+
 // Stage the slab [base, base + BS) of the A row: B-row starts / lengths / a_ij and the part prefix.
-// Ends with a barrier; returns the number of parts.
 template <int BS, bool kLoadVal, typename real>
 __device__ __forceinline__ int stage_parts(int t, int base, int a_end, const int *__restrict__ a_col,
                                            const real *__restrict__ a_val, const int *__restrict__ b_rpt,
@@ -177,73 +198,306 @@ __device__ __forceinline__ int stage_parts(int t, int base, int a_end, const int
     }
     s.kb[t] = kb;
     s.len[t] = len;
-    const int inc = group_inclusive_scan<BS>((len + kPartLen - 1) / kPartLen, t, s.wtot);
-    s.pre[t + 1] = inc;
-    if (t == 0) s.pre[0] = 0;
-    __syncthreads();
-    return s.pre[BS];
+    return scan_parts<BS, real>(t, kb, len, s);
 }
 
-// Walk the staged slab's parts.  The caller guarantees a barrier between stage_parts (or the
-// previous run_parts) and this call, and s.next == BS / 32 on entry; ends with a barrier that
-// also re-arms s.next.
+// first k in [lo, hi) with b_col[k] >= key (B rows are column-sorted)
+__device__ __forceinline__ int lower_bound_col(const int *__restrict__ b_col, int lo, int hi, int key)
+{
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (ld_nc(b_col + mid) < key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// stage_parts restricted to the products whose column lies in [col_lo, col_hi): the heavy kernels
+// walk a row of C in ascending column ranges (bitmap windows, accumulator chunks) and every product
+// is visited once per pass because the sub-range of each B row is found by binary search instead of
+// filtering.  use_lo / use_hi say which bounds actually cut (both false: the whole B row).
+// One thread per entry, both bounds from scratch: the path of rows with more than BS entries.
+template <int BS, bool kLoadVal, typename real>
+__device__ __forceinline__ int stage_parts_range(int t, int base, int a_end, const int *__restrict__ a_col,
+                                                 const real *__restrict__ a_val, const int *__restrict__ b_rpt,
+                                                 const int *__restrict__ b_col, int col_lo, int col_hi,
+                                                 bool use_lo, bool use_hi, PartScratch<BS, real> &s)
+{
+    int len = 0, kb = 0;
+    if (base + t < a_end) {
+        const int ac = ld_stream(a_col + base + t);
+        kb = ld_nc(b_rpt + ac);
+        int ke = ld_nc(b_rpt + ac + 1);
+        if (use_lo || use_hi) {
+            // the two searches run interleaved (independent load chains)
+            int l0 = kb, h0 = use_lo ? ke : kb, l1 = kb, h1 = use_hi ? ke : kb;
+            while ((l0 < h0) | (l1 < h1)) {
+                const int m0 = (l0 + h0) >> 1, m1 = (l1 + h1) >> 1;
+                const bool a0 = l0 < h0, a1 = l1 < h1;
+                const int c0 = a0 ? ld_nc(b_col + m0) : 0;
+                const int c1 = a1 ? ld_nc(b_col + m1) : 0;
+                if (a0) {
+                    if (c0 < col_lo) l0 = m0 + 1; else h0 = m0;
+                }
+                if (a1) {
+                    if (c1 < col_hi) l1 = m1 + 1; else h1 = m1;
+                }
+            }
+            if (use_hi) ke = l1;
+            if (use_lo) kb = l0;
+            if (ke < kb) ke = kb;
+        }
+        len = ke - kb;
+        if (kLoadVal) s.av[t] = ld_stream(a_val + base + t);
+    }
+    s.kb[t] = kb;
+    s.len[t] = len;
+    return scan_parts<BS, real>(t, kb, len, s);
+}
+
+// Lower bound by a GROUP of g = 2^glog lanes (g-ary search: ceil(log_{g+1} n) dependent loads instead
+// of log_2 n).  All 32 lanes of the warp call; lo / hi / key are uniform within a group; a group
+// with lo >= hi takes no part.  Returns the first k in [lo, hi) with b_col[k] >= key.
+__device__ __forceinline__ int group_lower_bound(const int *__restrict__ b_col, int lo, int hi, int key, int glog,
+                                                 int lane)
+{
+    const int g = 1 << glog;
+    const int gl = lane & (g - 1);
+    const int gfirst = lane & ~(g - 1);
+    const unsigned gmask = g == 32 ? 0xffffffffu : ((1u << g) - 1u);
+    while (__any_sync(0xffffffffu, lo < hi)) {
+        const int n = hi - lo;
+        const int step = n > 0 ? (int)(((unsigned)n + (unsigned)g) / (unsigned)(g + 1)) : 1;   // ceil(n / (g + 1)) >= 1
+        const int p = lo + gl * step + (step - 1);                                           // probe i = gl
+        const bool below = n > 0 && p < hi && ld_nc(b_col + p) < key;
+        const int m = __popc((__ballot_sync(0xffffffffu, below) >> gfirst) & gmask);
+        if (n > 0) {
+            // probes 0 .. m-1 are below the key, probe m (if inside) is not
+            const int nlo = lo + m * step;
+            const int nhi = m < g ? min(hi, nlo + step - 1) : hi;
+            lo = nlo;
+            hi = nhi;
+        }
+    }
+    return lo;
+}
+
+// ---- cursor staging for rows whose A entries fit one slab (E <= BS; 99.9 % of the heavy rows) ------
+// glog: log2 of the lanes that share an entry, min(5, log2(BS / pow2ceil(E))).
+__device__ __forceinline__ int entry_group_log(int E, int BS)
+{
+    int glog = 0;
+    while (glog < 5 && (E << (glog + 1)) <= BS) ++glog;
+    return glog;
+}
+
+// Window stage: segment of every B row inside the window [., c1).  first: the window is the first of
+// the row (segments start at the B row's start), otherwise they start where the previous window ended
+// (s.end).  cut_hi: the window does not reach N, so the end is searched.  Leaves kb/len = the window
+// segment, cur = its start, end = its end, and the part prefix.
+template <int BS, bool kLoadVal, typename real>
+__device__ __forceinline__ int stage_window(int t, int a_beg, int E, int glog, const int *__restrict__ a_col,
+                                            const real *__restrict__ a_val, const int *__restrict__ b_rpt,
+                                            const int *__restrict__ b_col, int c1, bool first, bool cut_hi,
+                                            PartScratch<BS, real> &s)
+{
+    const int e = t >> glog;
+    if (((t & ~31) >> glog) < E) {          // warp-uniform: this warp owns at least one entry
+        int lo = 0, hi = 0;
+        if (e < E) {
+            const int ac = ld_stream(a_col + a_beg + e);
+            lo = first ? ld_nc(b_rpt + ac) : s.end[e];
+            hi = ld_nc(b_rpt + ac + 1);
+        }
+        int res = hi;
+        if (cut_hi) res = group_lower_bound(b_col, lo, hi, c1, glog, t & 31);
+        if (e < E && (t & ((1 << glog) - 1)) == 0) {
+            s.kb[e] = lo;
+            s.len[e] = res - lo;
+            s.cur[e] = lo;
+            s.end[e] = res;
+            if (kLoadVal && first) s.av[e] = ld_stream(a_val + a_beg + e);
+        }
+    }
+    __syncthreads();
+    return scan_parts<BS, real>(t, t < E ? s.kb[t] : 0, t < E ? s.len[t] : 0, s);
+}
+
+// Chunk stage: segment [cur, first column >= col_hi) of every entry (last: up to the window end), and
+// the cursor moves on.
+template <int BS, typename real>
+__device__ __forceinline__ int stage_chunk(int t, int E, int glog, const int *__restrict__ b_col, int col_hi,
+                                           bool last, PartScratch<BS, real> &s)
+{
+    const int e = t >> glog;
+    if (((t & ~31) >> glog) < E) {
+        int lo = 0, hi = 0;
+        if (e < E) {
+            lo = s.cur[e];
+            hi = s.end[e];
+        }
+        int res = hi;
+        if (!last) res = group_lower_bound(b_col, lo, hi, col_hi, glog, t & 31);
+        if (e < E && (t & ((1 << glog) - 1)) == 0) {
+            s.kb[e] = lo;
+            s.len[e] = res - lo;
+            s.cur[e] = res;
+        }
+    }
+    __syncthreads();
+    return scan_parts<BS, real>(t, t < E ? s.kb[t] : 0, t < E ? s.len[t] : 0, s);
+}
+
+// entry of part q = largest e with pre[e] <= q (two ballots: 32-ary search over pre1, then over pre)
+template <int BS, typename real>
+__device__ __forceinline__ int part_entry(const PartScratch<BS, real> &s, int q, int lane)
+{
+    static_assert(BS == 1024, "two-level 32-ary entry search");
+    const unsigned q1 = __ballot_sync(0xffffffffu, s.pre1[lane] <= q);
+    const int e = (__popc(q1) - 1) * 32;
+    const unsigned q2 = __ballot_sync(0xffffffffu, s.pre[e + lane] <= q);
+    return e + __popc(q2) - 1;
+}
+
+// Walk the staged slab's parts (value pass: lane-strided, so that the 32 products of one instruction
+// have 32 different ranks); the caller guarantees a barrier between the staging and this call.
+// Ends with a barrier.  Both kernels are ISSUE-bound once the shared-memory conflicts are gone
+// (profiles/r1_ncu_bitmap_s20_v3.txt: 63 % issue-slot utilisation, 8 warp instructions per product),
+// so full parts -- four out of five -- run without any per-element predicate.
 template <int BS, bool kNumeric, typename real, typename F>
 __device__ __forceinline__ void run_parts(int t, int total, const int *__restrict__ b_col,
                                           const real *__restrict__ b_val, PartScratch<BS, real> &s, F &&f)
 {
     constexpr int NW = BS / 32;
-    constexpr int S1 = BS / 32;   // level-1 stride of the 32-ary entry search
+    constexpr int U = kPartLen / 32;
     const int lane = t & 31;
-    int q = t >> 5;
-    while (q < total) {
-        // entry of part q = largest e with pre[e] <= q
-        const unsigned q1 = __ballot_sync(0xffffffffu, s.pre[lane * S1] <= q);
-        int e = (__popc(q1) - 1) * S1;
-        if (S1 > 1) {
-            const unsigned q2 = __ballot_sync(0xffffffffu, lane < S1 && s.pre[e + lane] <= q);
-            e += __popc(q2) - 1;
-        }
-        const int k0 = s.kb[e] + (q - s.pre[e]) * kPartLen;
-        const int k1 = min(s.kb[e] + s.len[e], k0 + kPartLen);
+    for (int q = t >> 5; q < total; q += NW) {
+        const int e = part_entry<BS, real>(s, q, lane);
+        const int kb = s.kb[e];
+        const int ke = kb + s.len[e];
+        const int p0 = (kb & ~3) + (q - s.pre[e]) * kPartLen;     // first element of the part
         const real av = kNumeric ? s.av[e] : real(0);
-#pragma unroll 1
-        for (int k = k0 + lane; k < k1; k += 128) {
-            int c[4];
-            real v[4];
+        const int *pc = b_col + p0 + lane;
+        const real *pv = b_val + p0 + lane;
+        int c[U];
+        real v[U];
+        if (p0 >= kb && p0 + kPartLen <= ke) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int kk = k + 32 * u;
+            for (int u = 0; u < U; ++u) {
+                c[u] = ld_nc(pc + 32 * u);
+                if (kNumeric) v[u] = ld_nc(pv + 32 * u);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) f(c[u], kNumeric ? av * v[u] : real(0));
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int kk = p0 + lane + 32 * u;
                 c[u] = -1;
-                if (kk < k1) {
-                    c[u] = ld_nc(b_col + kk);
-                    if (kNumeric) v[u] = av * ld_nc(b_val + kk);
+                if (kk >= kb && kk < ke) {
+                    c[u] = ld_nc(pc + 32 * u);
+                    if (kNumeric) v[u] = ld_nc(pv + 32 * u);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (c[u] >= 0) f(c[u], kNumeric ? v[u] : real(0));
+            for (int u = 0; u < U; ++u)
+                if (c[u] >= 0) f(c[u], kNumeric ? av * v[u] : real(0));
         }
-        if (lane == 0) q = atomicAdd(&s.next, 1);
-        q = __shfl_sync(0xffffffffu, q, 0);
     }
     __syncthreads();
-    if (t == 0) s.next = NW;
 }
 
-template <int BS, bool kNumeric, typename real, typename F>
-__device__ __forceinline__ void for_each_product_parts(int t, int a_beg, int a_end,
-                                                       const int *__restrict__ a_col,
-                                                       const real *__restrict__ a_val,
-                                                       const int *__restrict__ b_rpt,
-                                                       const int *__restrict__ b_col,
-                                                       const real *__restrict__ b_val,
-                                                       PartScratch<BS, real> &s, F &&f)
+// ---------------------------------------------------------------------------------------------
+// Column bitmap of the heavy kernels: plain bit order (column cc of the window is bit cc & 31 of
+// 32-bit word cc >> 5); the 64-bit word PAIRS are swizzled inside every batch of 32 pairs (2048
+// columns): pair j of batch b lives at j ^ h(b), h(b) = (b ^ (b >> 5)) & 31.  Graph generators such as
+// R-MAT make every bit of a column index 0 with probability ~0.76, so a quarter of ALL products share
+// any given 5-bit field of the column index and would hit one bank (measured: 14 wavefronts per
+// shared-memory atomic instead of ~3); after the swizzle the bank depends on the column bits 6..20.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned bitmap_swz(unsigned batch) { return (batch ^ (batch >> 5)) & 31u; }
+
+// physical index of logical 32-bit word w32 (= cc >> 5)
+__device__ __forceinline__ unsigned bitmap_word32(unsigned w32)
 {
-    for (int base = a_beg; base < a_end; base += BS) {
-        if (t == 0) s.next = BS / 32;      // ordered before the claims by stage_parts' barriers
-        const int total = stage_parts<BS, kNumeric, real>(t, base, a_end, a_col, a_val, b_rpt, s);
-        run_parts<BS, kNumeric, real>(t, total, b_col, b_val, s, f);
+    return w32 ^ (((w32 >> 5) ^ (w32 >> 10)) & 0x3eu);
+}
+
+// Mark pass over the staged parts.  Every lane reads FOUR CONSECUTIVE products per 128-bit load (two
+// loads per part, all in flight together), merges the bits that fall into the same 32-bit word in
+// registers, and issues one shared-memory atomicOr per distinct word: a dense B row (hub vertex)
+// costs one atomic per four products and an 8-way instead of a 32-way same-word conflict, a sparse one
+// costs what it did.  b_vec_end: largest index k (multiple of 4) such that b_col[k .. k+3] may be read
+// with one load (0 disables the vector path, e.g. for a misaligned B.col).  c0 / ncols: the window;
+// kFilter drops columns outside it (unsorted B).
+template <bool kChecked, bool kFilter>
+__device__ __forceinline__ void mark4(unsigned *bm32, const int4 c, int k, int kb, int ke, int c0, unsigned ncols)
+{
+    const int col[4] = {c.x, c.y, c.z, c.w};
+    unsigned w[4], m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned cc = (unsigned)(col[j] - c0);
+        bool ok = true;
+        if (kChecked) ok = k + j >= kb && k + j < ke;
+        if (kFilter) ok = ok && cc < ncols;
+        w[j] = (kChecked || kFilter) ? (ok ? cc >> 5 : 0xffffffffu) : cc >> 5;
+        m[j] = 1u << (cc & 31u);
     }
+#pragma unroll
+    for (int j = 1; j < 4; ++j) {
+        if (w[j] == w[j - 1]) {          // same word as the predecessor: hand its bits on
+            m[j] |= m[j - 1];
+            w[j - 1] = 0xffffffffu;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (w[j] != 0xffffffffu) atomicOr(bm32 + bitmap_word32(w[j]), m[j]);
+}
+
+template <int BS, bool kFilter, typename real>
+__device__ __forceinline__ void run_parts_mark(int t, int total, const int *__restrict__ b_col, int b_vec_end,
+                                               PartScratch<BS, real> &s, unsigned *bm32, int c0, unsigned ncols)
+{
+    constexpr int NW = BS / 32;
+    constexpr int U = kPartLen / 128;
+    const int lane = t & 31;
+    for (int q = t >> 5; q < total; q += NW) {
+        const int e = part_entry<BS, real>(s, q, lane);
+        const int kb = s.kb[e];
+        const int ke = kb + s.len[e];
+        const int p0 = (kb & ~3) + (q - s.pre[e]) * kPartLen;
+        const int k0 = p0 + 4 * lane;
+        int4 c[U];
+        if (p0 >= kb && p0 + kPartLen <= ke && p0 + kPartLen <= b_vec_end) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) c[u] = __ldg(reinterpret_cast<const int4 *>(b_col + k0 + 128 * u));
+#pragma unroll
+            for (int u = 0; u < U; ++u) mark4<false, kFilter>(bm32, c[u], 0, 0, 0, c0, ncols);
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = k0 + 128 * u;
+                c[u] = make_int4(0, 0, 0, 0);
+                if (k < ke) {
+                    if (k + 4 <= b_vec_end) {
+                        c[u] = __ldg(reinterpret_cast<const int4 *>(b_col + k));
+                    } else {
+                        c[u].x = ld_nc(b_col + k);
+                        if (k + 1 < ke) c[u].y = ld_nc(b_col + k + 1);
+                        if (k + 2 < ke) c[u].z = ld_nc(b_col + k + 2);
+                        if (k + 3 < ke) c[u].w = ld_nc(b_col + k + 3);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) mark4<true, kFilter>(bm32, c[u], k0 + 128 * u, kb, ke, c0, ncols);
+        }
+    }
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -136,33 +136,69 @@ num_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
     }
 }
 
-// ---- bitmap + rank class ------------------------------------------------------------------------
-// shared memory: bm[nw] 64-bit bitmap words of the column tile, pre[nw] exclusive popcount prefix.
-// Every warp owns a contiguous segment of the words (lanes interleaved, so the 8-byte reads are
-// bank-conflict free): the prefix needs two barriers per tile whatever N is, and a lane emits the
-// columns of its words as one contiguous run of C.col.
-template <typename real, int BS, bool kSingle>
+// ---- bitmap + rank + shared-memory accumulator class ---------------------------------------------
+// A row of C is produced in ascending column WINDOWS of W = 2^wshift columns and, inside a window,
+// in CHUNKS of at most `cap` output entries:
+//   mark     every product of the window sets its column's bit (run_parts_mark: 128-bit loads, bits
+//            merged per word in registers, one shared-memory atomicOr per distinct word);
+//   rank     one sweep over the bitmap, a batch of 32 word pairs (2048 columns) per warp step: 16-bit
+//            exclusive popcount prefix of every 32-bit word inside its batch, outputs per batch, then a
+//            CTA-wide exclusive scan of the batch totals.  rank(col) = batch base + word prefix +
+//            popcount of the bits below;
+//   per chunk
+//     columns  every warp claims batches, writes the columns of their set bits into a staging
+//              buffer at rank - chunk base, and the CTA copies the buffer to C.col with coalesced stores;
+//     values   acc[0..cap) (the same shared memory) is zeroed, every product whose column lies in the
+//              chunk's column range is added at acc[rank - chunk base] with a shared-memory atomic
+//              (measured on B200: 1.0 T adds/s fp32, 0.55 T/s fp64, against 0.22 T/s for the
+//              red.global the first version used, scripts/micro/atomics_bench.cu), and acc is copied
+//              to C.val with coalesced stores.
+// Every product is read once per pass whatever the number of windows and chunks: the sub-range of each
+// B row that falls into a column range is found by searching the sorted B row (stage_window /
+// stage_chunk keep a cursor per entry; rows with more than 1024 entries search from scratch).
+// Shared memory: W/8 bitmap + W/16 prefixes + cap * max(4, sizeof(real)) staging / accumulators.
+constexpr int kMaxChunks = 512;
+constexpr int kMaxBatches = 256;            // W <= 2^19: 2048 columns per batch
+
+// n-th (0-based) set bit of x
+__device__ __forceinline__ int select32(unsigned x, int n)
+{
+    for (int i = 0; i < n; ++i) x &= x - 1;
+    return __ffs((int)x) - 1;
+}
+
+// kSorted: the rows of B are column-sorted (checked once per call on the device); otherwise -- the
+// reference reader leaves the rows of symmetric files unsorted (nsparse.cu:115-123) -- every pass walks
+// the whole B rows and filters by column range.
+template <typename real, int BS, bool kSorted>
 __global__ void __launch_bounds__(BS, 1)
 num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                   const real *__restrict__ a_val, const int *__restrict__ b_rpt,
                   const int *__restrict__ b_col, const real *__restrict__ b_val,
                   const long long *__restrict__ c_rpt, int *__restrict__ c_col, real *__restrict__ c_val,
                   const int *__restrict__ row_perm, int *__restrict__ bins, int bin_lo, int bin_hi,
-                  int queue, int N, int tile_cols, int dbg)
+                  int queue, int N, int wshift, int cap, int b_vec_end, int dbg)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = BS / 32;
+    static_assert(NW == 32, "the batch scan and the entry search assume 32 warps");
     __shared__ PartScratch<BS, real> s_part;
-    __shared__ int s_row;
-    __shared__ int s_wsum[NW];
-    const int tile_words = (tile_cols + 63) >> 6;
-    unsigned long long *bm = reinterpret_cast<unsigned long long *>(smem_raw);
+    __shared__ int s_row, s_next;
+    __shared__ int s_batch[kMaxBatches + 1];    // outputs before the batch (exclusive), window relative
+    __shared__ int s_bound[kMaxChunks + 1];
+    const unsigned W = 1u << wshift;
+    const int nbatch = (int)(W >> 11);          // a batch = 32 word pairs = 2048 columns
+    uint2 *bm64 = reinterpret_cast<uint2 *>(smem_raw);
     unsigned *bm32 = reinterpret_cast<unsigned *>(smem_raw);
-    int *pre = reinterpret_cast<int *>(smem_raw + sizeof(unsigned long long) * (size_t)((tile_words + 1) & ~1));
+    unsigned *pre2 = reinterpret_cast<unsigned *>(smem_raw + (W >> 3));            // per pair: two 16-bit prefixes
+    const unsigned short *pre16 = reinterpret_cast<const unsigned short *>(pre2);  // the same per 32-bit word
+    real *acc = reinterpret_cast<real *>(smem_raw + (W >> 3) + (W >> 4));
+    int *stg = reinterpret_cast<int *>(acc);    // column staging aliases the accumulators
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     int lo, hi;
     class_range(bins, bin_lo, bin_hi, lo, hi);
     const int n = hi - lo;
+    const int nwin = (int)(((unsigned)N + W - 1u) >> wshift);
     while (true) {
         if (t == 0) s_row = atomicAdd(&bins[kBinQueue + queue], 1);
         __syncthreads();
@@ -170,106 +206,161 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
         if (r >= n) break;
         const int rid = row_perm[lo + r];
         const int a_beg = a_rpt[rid], a_end = a_rpt[rid + 1];
+        const int E = a_end - a_beg;
+        const bool one_slab = E <= BS;
+        const int glog = entry_group_log(E, BS);
         long long out = c_rpt[rid];
-        for (int t0 = 0; t0 < N; t0 += tile_cols) {
-            const int ncols = min(tile_cols, N - t0);
-            const int nw = (ncols + 63) >> 6;
+        for (int win = 0; win < nwin; ++win) {
+            const int c0 = (int)((unsigned)win << wshift);
+            const int c1 = (int)min((unsigned)N, (unsigned)c0 + W);
+            const bool cut_lo = kSorted && win > 0, cut_hi = kSorted && win < nwin - 1;
             {
-                uint4 *bm4 = reinterpret_cast<uint4 *>(bm);
-                const int nw4 = (nw + 1) >> 1;
-                for (int i = t; i < nw4; i += BS) bm4[i] = make_uint4(0u, 0u, 0u, 0u);
+                uint4 *bm4 = reinterpret_cast<uint4 *>(smem_raw);
+                for (int i = t; i < (int)(W >> 7); i += BS) bm4[i] = make_uint4(0u, 0u, 0u, 0u);
             }
             __syncthreads();
-            // pass 1: structure of the tile.  A row whose A entries fit one slab (nearly all) is
-            // staged once, with its values, and pass 2 walks the same staged parts again.
-            const bool one_slab = a_end - a_beg <= BS;
+            // ---- mark ----
             int staged_total = 0;
-            auto mark = [&](int c, real) {
-                const unsigned cc = (unsigned)(c - t0);
-                if (kSingle || cc < (unsigned)ncols) {
-                    const unsigned bit = 1u << (cc & 31);
-                    unsigned *w = bm32 + (cc >> 5);
-                    if (!(*((volatile unsigned *)w) & bit)) atomicOr(w, bit);
-                }
-            };
+            const unsigned ncols = (unsigned)(c1 - c0);
             if (one_slab) {
-                if (t == 0) s_part.next = NW;
-                staged_total = stage_parts<BS, true, real>(t, a_beg, a_end, a_col, a_val, b_rpt, s_part);
-                run_parts<BS, false, real>(t, staged_total, b_col, b_val, s_part, mark);
+                staged_total = stage_window<BS, true, real>(t, a_beg, E, glog, a_col, a_val, b_rpt, b_col, c1,
+                                                            win == 0 || !kSorted, cut_hi, s_part);
+                run_parts_mark<BS, !kSorted, real>(t, staged_total, b_col, b_vec_end, s_part, bm32, c0, ncols);
             } else {
-                for_each_product_parts<BS, false, real>(t, a_beg, a_end, a_col, a_val, b_rpt, b_col, b_val, s_part,
-                                                        mark);
+                for (int base = a_beg; base < a_end; base += BS) {
+                    const int total = stage_parts_range<BS, false, real>(t, base, a_end, a_col, a_val, b_rpt, b_col, c0,
+                                                                         c1, cut_lo, cut_hi, s_part);
+                    run_parts_mark<BS, !kSorted, real>(t, total, b_col, b_vec_end, s_part, bm32, c0, ncols);
+                }
             }
-            // exclusive prefix of the per-word popcounts: warp totals, then per-warp running scan
-            const int seg = ((nw + BS - 1) / BS) * 32;         // words per warp (multiple of 32)
-            const int w0 = wid * seg, w1 = min(nw, w0 + seg);
-            int tot = 0;
-            for (int j = w0 + lane; j < w1; j += 32) tot += __popcll(bm[j]);
-            tot = warp_sum(tot);
-            if (lane == 0) s_wsum[wid] = tot;
-            __syncthreads();
-            int carry, tile_nnz;
-            {
-                const int ws = lane < NW ? s_wsum[lane] : 0;
-                carry = warp_sum(lane < wid ? ws : 0);
-                tile_nnz = warp_sum(ws);
-            }
-            for (int jb = w0; jb < w1; jb += 32) {
-                const int j = jb + lane;
-                const int c = j < w1 ? __popcll(bm[j]) : 0;
+            // ---- rank: per-word prefixes inside every batch, batch totals, CTA-wide exclusive scan ----
+            for (int b = wid; b < nbatch; b += NW) {
+                const unsigned pj = (unsigned)(b << 5) | ((unsigned)lane ^ bitmap_swz((unsigned)b));
+                const uint2 wd = bm64[pj];
+                const int cl = __popc(wd.x);
+                const int c = cl + __popc(wd.y);
                 int inc = c;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const int v = __shfl_up_sync(0xffffffffu, inc, o);
                     if (lane >= o) inc += v;
                 }
-                if (j < w1) pre[j] = carry + inc - c;
-                carry += __shfl_sync(0xffffffffu, inc, 31);
-            }
-            // values start at zero (coalesced), columns come straight from the bitmap (sorted)
-            if (!(dbg & 4)) for (int i = t; i < tile_nnz; i += BS) c_val[out + i] = real(0);
-            if (!(dbg & 1)) {
-                int *crow = c_col + out;
-                for (int jb = w0; jb < w1; jb += 32) {
-                    const int j = jb + lane;
-                    if (j < w1) {
-                        // 32-bit halves, 32-bit output index: ~9 instructions per emitted column
-                        unsigned lo32 = bm32[2 * j], hi32 = bm32[2 * j + 1];
-                        int idx = pre[j];
-                        const int cbase = t0 + (j << 6);
-                        while (lo32) {
-                            crow[idx++] = cbase + __ffs((int)lo32) - 1;
-                            lo32 &= lo32 - 1;
-                        }
-                        while (hi32) {
-                            crow[idx++] = cbase + 31 + __ffs((int)hi32);
-                            hi32 &= hi32 - 1;
-                        }
-                    }
-                }
+                const unsigned ex = (unsigned)(inc - c);
+                pre2[pj] = ex | ((ex + (unsigned)cl) << 16);
+                if (lane == 31) s_batch[b] = inc;
             }
             __syncthreads();
-            // pass 2: values
-            real *cv = c_val + out;
-            auto add = [&](int c, real v) {
-                const unsigned cc = (unsigned)(c - t0);
-                if (kSingle || cc < (unsigned)ncols) {
-                    // rank = prefix of the 64-bit word + set bits below cc, in 32-bit operations
-                    const unsigned w = cc >> 6;
-                    const uint2 word = *reinterpret_cast<const uint2 *>(bm + w);
-                    const unsigned below = (1u << (cc & 31)) - 1u;
-                    const bool upper = (cc & 32) != 0;
-                    const int rank = pre[w] + __popc(word.x & (upper ? 0xffffffffu : below)) +
-                                     __popc(word.y & (upper ? below : 0u));
-                    atomicAdd(cv + rank, v);
+            int tile_nnz;
+            {
+                const int v = t < nbatch ? s_batch[t] : 0;
+                const int inc = group_inclusive_scan<BS>(v, t, s_part.wtot);
+                __syncthreads();                       // everyone has read its count and the warp totals
+                if (t < nbatch) s_batch[t] = inc - v;
+                if (t == BS - 1) s_batch[nbatch] = inc;
+                __syncthreads();
+                tile_nnz = s_batch[nbatch];
+            }
+            const int nch = (tile_nnz + cap - 1) / cap;
+            // chunk boundary columns: chunk k starts at the column of rank k * cap (one warp per boundary)
+            for (int k = 1 + wid; k < nch; k += NW) {
+                const int R = k * cap;
+                // batch: largest b with s_batch[b] <= R  (nbatch <= 256: 8 entries per lane)
+                int cntb = 0;
+                for (int i = lane; i < nbatch; i += 32) cntb += s_batch[i] <= R;
+                const int b = warp_sum(cntb) - 1;
+                const unsigned pj = (unsigned)(b << 5) | ((unsigned)lane ^ bitmap_swz((unsigned)b));
+                const uint2 wd = bm64[pj];
+                const unsigned pp = pre2[pj];
+                const int rb = R - s_batch[b];                      // rank inside the batch
+                const int p_lo = (int)(pp & 0xffffu), p_hi = (int)(pp >> 16);
+                const int p_end = p_hi + __popc(wd.y);
+                if (rb >= p_lo && rb < p_end) {                     // exactly one lane
+                    const int colw = rb < p_hi ? select32(wd.x, rb - p_lo) : 32 + select32(wd.y, rb - p_hi);
+                    s_bound[k] = c0 + (((b << 5) + lane) << 6) + colw;
                 }
-            };
-            if (dbg & 2) {
-            } else if (one_slab)
-                run_parts<BS, true, real>(t, staged_total, b_col, b_val, s_part, add);
-            else
-                for_each_product_parts<BS, true, real>(t, a_beg, a_end, a_col, a_val, b_rpt, b_col, b_val, s_part,
-                                                       add);
+            }
+            if (t == 0) s_next = 0;
+            __syncthreads();
+            // ---- chunk by chunk: columns, then values ----
+            for (int k = 0; k < nch; ++k) {
+                const int r0 = k * cap;
+                const int cnt = min(tile_nnz - r0, cap);
+                const int col_lo = k > 0 ? s_bound[k] : c0;
+                const int col_hi = k < nch - 1 ? s_bound[k + 1] : c1;
+                if (!(dbg & 1)) {
+                    // Batches are CLAIMED: a skewed row keeps its dense batches where the batch index has
+                    // few one bits, and any static deal by batch index inherits that skew.
+                    while (true) {
+                        int b = 0;
+                        if (lane == 0) b = atomicAdd(&s_next, 1);
+                        b = __shfl_sync(0xffffffffu, b, 0);
+                        if (b >= nbatch) break;
+                        const int base = s_batch[b] - r0;
+                        const int bend = s_batch[b + 1] - r0;
+                        if (bend <= 0 || base >= cnt || bend == base) continue;      // no output of this chunk
+                        const unsigned pj = (unsigned)(b << 5) | ((unsigned)lane ^ bitmap_swz((unsigned)b));
+                        uint2 wd = bm64[pj];
+                        int pos = base + (int)(pre2[pj] & 0xffffu);
+                        const int cbase = c0 + (((b << 5) + lane) << 6);
+                        if (base >= 0 && bend <= cnt) {
+                            while (wd.x) {
+                                stg[pos++] = cbase + __ffs((int)wd.x) - 1;
+                                wd.x &= wd.x - 1;
+                            }
+                            while (wd.y) {
+                                stg[pos++] = cbase + 31 + __ffs((int)wd.y);
+                                wd.y &= wd.y - 1;
+                            }
+                        } else {                                   // batch straddles a chunk boundary
+                            while (wd.x) {
+                                if ((unsigned)pos < (unsigned)cnt) stg[pos] = cbase + __ffs((int)wd.x) - 1;
+                                ++pos;
+                                wd.x &= wd.x - 1;
+                            }
+                            while (wd.y) {
+                                if ((unsigned)pos < (unsigned)cnt) stg[pos] = cbase + 31 + __ffs((int)wd.y);
+                                ++pos;
+                                wd.y &= wd.y - 1;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    if (t == 0) s_next = 0;
+                    int *cc = c_col + out + r0;
+                    for (int i = t; i < cnt; i += BS) cc[i] = stg[i];
+                    __syncthreads();
+                }
+                if (dbg & 2) continue;
+                for (int i = t; i < cnt; i += BS) acc[i] = real(0);
+                // (the barriers of the staging below order the zeroes before the adds)
+                auto add = [&](int c, real v) {
+                    if (!kSorted && (unsigned)(c - col_lo) >= (unsigned)(col_hi - col_lo)) return;
+                    const unsigned cc = (unsigned)(c - c0);
+                    const unsigned w32 = cc >> 5;
+                    const unsigned p32 = bitmap_word32(w32);
+                    const int rank = s_batch[w32 >> 6] + (int)pre16[p32] +
+                                     __popc(bm32[p32] & ((1u << (cc & 31u)) - 1u));
+                    atomicAdd(acc + (rank - r0), v);
+                };
+                if (one_slab) {
+                    int total = staged_total;              // one chunk (or unsorted B): the mark pass staged it
+                    if (kSorted && nch > 1)
+                        total = stage_chunk<BS, real>(t, E, glog, b_col, col_hi, k == nch - 1, s_part);
+                    else
+                        __syncthreads();
+                    run_parts<BS, true, real>(t, total, b_col, b_val, s_part, add);
+                } else {
+                    for (int base = a_beg; base < a_end; base += BS) {
+                        const int total = stage_parts_range<BS, true, real>(
+                            t, base, a_end, a_col, a_val, b_rpt, b_col, col_lo, col_hi, kSorted && (cut_lo || k > 0),
+                            kSorted && (cut_hi || k < nch - 1), s_part);
+                        run_parts<BS, true, real>(t, total, b_col, b_val, s_part, add);
+                    }
+                }
+                real *cv = c_val + out + r0;
+                for (int i = t; i < cnt; i += BS) cv[i] = acc[i];
+                __syncthreads();                       // the next chunk's columns reuse the buffer
+            }
             out += tile_nnz;
         }
     }
@@ -283,6 +374,13 @@ static inline long long num_rows_in(const nsp_spgemm_state &sp, int bin_lo, int 
     long long n = 0;
     for (int b = bin_lo; b <= bin_hi; ++b) n += sp.h_bins[kBinHist + b];
     return n;
+}
+
+// see run_parts_mark: last index from which B.col may be read with a 128-bit load (0: never)
+static inline int b_vec_end_of(const nsp_context *ctx, const int *b_col)
+{
+    if ((reinterpret_cast<uintptr_t>(b_col) & 15u) != 0 || ctx->opt_no_vec) return 0;
+    return (int)(ctx->sp.b_nnz & ~3ll);
 }
 
 static inline int num_imin(long long a, long long b) { return (int)(a < b ? a : b); }
@@ -338,12 +436,23 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
     //   bins 8..9      <= 8192      CTA(1024) / row, <= 16384 slots (128 KiB fp32 / 192 KiB fp64)
     //   bins >= bm_bin              CTA(1024) / row, bitmap + rank over column tiles
     const int smem_cap = ctx->max_smem_optin - kStaticSmemReserve;
-    const int tile_max = ((smem_cap - 64) / 24) * 128;
-    const int tile_cols = N < tile_max ? ((N + 127) / 128) * 128 : tile_max;
+    // window: power of two >= N, at least 2^16 (one prefix segment of >= 32 words per warp), at most
+    // 2^ws_max; 3/16 byte per column for bitmap + prefixes, the rest of the CTA's shared memory holds
+    // the accumulators
+    int ws_max = ctx->opt_num_window_shift > 0 ? (int)ctx->opt_num_window_shift : 19;
+    if (ws_max < 16) ws_max = 16;
+    if (ws_max > 19) ws_max = 19;
+    int wshift = 16;
+    while (wshift < ws_max && (1ll << wshift) < (long long)N) ++wshift;
+    const size_t fixed = ((size_t)3 << wshift) / 16;
+    int cap = (int)((smem_cap - (long long)fixed) / (long long)sizeof(real));
+    cap &= ~127;
+    if (cap > 32768) cap = 32768;
+    const bool one_window = (1ll << wshift) >= (long long)N;
     const int slot_bytes = 4 + (int)sizeof(real);
     int bm_bin = 10;
-    if (N <= tile_max) {
-        // single tile: bitmap + rank needs no sort, the hash path pays an O(n log^2 n) bitonic sort
+    if (one_window) {
+        // single window: bitmap + rank needs no sort, the hash path pays an O(n log^2 n) bitonic sort
         // per row; measured crossover on R-MAT ~N/1024 entries per row
         const int v = N / 1024 + 1;
         bm_bin = log_bin(v, kNumShift) + 1;
@@ -357,13 +466,15 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
     }
     const int sms = ctx->sm_count;
     if (num_rows_in(sp, bm_bin, kNumBins - 1) > 0) {
-        const size_t tw = (size_t)(tile_cols + 63) / 64;
-        const size_t smem = ((tw + 1) & ~size_t(1)) * 8 + tw * 4 + 16;
+        if (cap < 1024 || ((1ll << wshift) + cap - 1) / cap > kMaxChunks)
+            return ctx->fail(-4, "nsp_spgemm_numeric: shared memory too small for the bitmap kernel");
+        const size_t smem = fixed + (size_t)cap * sizeof(real);
         const int grid = num_imin(num_rows_in(sp, bm_bin, kNumBins - 1), (long long)sms);
-        auto kern = N <= tile_max ? num_bitmap_kernel<real, 1024, true> : num_bitmap_kernel<real, 1024, false>;
+        auto kern = sp.b_sorted ? num_bitmap_kernel<real, 1024, true> : num_bitmap_kernel<real, 1024, false>;
         NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         num_prof_class(ctx, "num_bitmap", bm_bin, kNumBins - 1);
-        kern<<<grid, 1024, smem, ctx->stream>>>(NSP_NUM_ARGS, bm_bin, kNumBins - 1, 4, N, tile_cols, (int)ctx->opt_debug);
+        kern<<<grid, 1024, smem, ctx->stream>>>(NSP_NUM_ARGS, bm_bin, kNumBins - 1, 4, N, wshift, cap,
+                                                b_vec_end_of(ctx, b_col), (int)ctx->opt_debug);
         ctx->prof_end();
         ctx->launches += 1;
         NSP_CUDA_TRY(ctx, cudaGetLastError());

@@ -130,6 +130,27 @@ hist_kernel(const int *__restrict__ values, const int *__restrict__ row_ip,
     }
 }
 
+// Are the rows of B column-sorted (non-decreasing)?  unsorted = descents over the whole column array
+// minus the descents that sit on a row boundary.  The heavy kernels cut B rows by column range with
+// binary searches when they are, and fall back to filtering when not.
+__global__ void __launch_bounds__(256)
+check_b_sorted_kernel(const int *__restrict__ b_rpt, const int *__restrict__ b_col, int K,
+                      unsigned long long *__restrict__ unsorted)
+{
+    const long long nnz = b_rpt[K];
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    long long d = 0;
+    for (long long k = tid + 1; k < nnz; k += nth) d += b_col[k] < b_col[k - 1];
+    for (long long i = tid + 1; i < K; i += nth) {
+        const int s = b_rpt[i];
+        if (s > 0 && s < b_rpt[i + 1]) d -= b_col[s] < b_col[s - 1];
+    }
+    d = warp_sum_ll(d);
+    if ((threadIdx.x & 31) == 0 && d) atomicAdd(unsorted, (unsigned long long)d);
+    if (tid == 0) unsorted[kScalarNnzB - kScalarUnsorted] = (unsigned long long)nnz;
+}
+
 // start[b] = number of rows in bins heavier than b; also clears cursors and queue heads.
 __global__ void bin_offsets_kernel(int *bins)
 {
@@ -310,8 +331,8 @@ static int plan_fetch(nsp_context *ctx)
 }
 
 // ip per row (capped at `cap`), histogram, offsets, permutation.
-int plan_by_intprod(nsp_context *ctx, int M, int cap, const int *a_rpt, const int *a_col,
-                    const int *b_rpt)
+int plan_by_intprod(nsp_context *ctx, int M, int K, int cap, const int *a_rpt, const int *a_col,
+                    const int *b_rpt, const int *b_col)
 {
     nsp_spgemm_state &sp = ctx->sp;
     cudaStream_t st = ctx->stream;
@@ -326,9 +347,17 @@ int plan_by_intprod(nsp_context *ctx, int M, int cap, const int *a_rpt, const in
         bin_offsets_kernel<<<1, 32, 0, st>>>(sp.d_bins);
         scatter_rows_kernel<<<grid, 256, 0, st>>>(sp.d_row_ip, M, cap, kSymShift, sp.d_bins, sp.d_row_perm);
         ctx->launches += 3;
+        if (K > 0) {
+            check_b_sorted_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(
+                b_rpt, b_col, K, (unsigned long long *)(sp.d_scalars + kScalarUnsorted));
+            ctx->launches += 1;
+        }
     }
     NSP_CUDA_TRY(ctx, cudaGetLastError());
-    return plan_fetch(ctx);
+    if (plan_fetch(ctx) != 0) return -1;
+    sp.b_sorted = sp.h_scalars[kScalarUnsorted] == 0;
+    sp.b_nnz = K > 0 && M > 0 ? sp.h_scalars[kScalarNnzB] : 0;
+    return 0;
 }
 
 int plan_by_count(nsp_context *ctx, int M, int shift, const int *a_rpt)

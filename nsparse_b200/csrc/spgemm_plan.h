@@ -24,6 +24,8 @@ constexpr int kSumInts = 96;
 // d_scalars layout (long long)
 constexpr int kScalarIp = 0;     // total intermediate products (uncapped)
 constexpr int kScalarNnz = 1;    // nnz(C)
+constexpr int kScalarNnzB = 3;     // B.rpt[K]
+constexpr int kScalarUnsorted = 2;   // entries of B below their predecessor in the same row
 
 // Bin shifts: symbolic bins rows by min(intermediate products, N) with bin 0 = "<= 32"
 // (IMB_PWMIN of the reference), numeric bins by nnz(C_i) with bin 0 = "<= 16" (B_PWMIN).
@@ -39,8 +41,8 @@ __device__ __forceinline__ void class_range(const int *bins, int bin_lo, int bin
 }
 
 int plan_reserve(nsp_context *ctx, int M);
-int plan_by_intprod(nsp_context *ctx, int M, int cap, const int *a_rpt, const int *a_col,
-                    const int *b_rpt);
+int plan_by_intprod(nsp_context *ctx, int M, int K, int cap, const int *a_rpt, const int *a_col,
+                    const int *b_rpt, const int *b_col);
 int plan_by_count(nsp_context *ctx, int M, int shift, const int *a_rpt);
 int scan_row_counts(nsp_context *ctx, int M, long long *rpt64);
 

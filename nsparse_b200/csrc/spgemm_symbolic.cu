@@ -114,25 +114,32 @@ sym_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
     }
 }
 
-// ---- bitmap class: one CTA per row, one pass over the row's products per column tile -------------
-// kSingle: the whole row fits one tile (N <= tile_cols), no column-range test per product.
-// New columns are counted where they are inserted (the old word of the atomicOr says whether the
-// bit was new), so there is no popcount pass over the N/32 words afterwards.
-template <int BS, bool kSingle>
+// ---- bitmap class: one CTA per row, one pass over the row's products per column window -----------
+// Window of W = 2^wshift columns (W/8 bytes of shared memory, up to 2^20).  Every product sets its bit
+// with one shared-memory atomicOr in the block-transposed layout (spgemm_device.cuh), the row's count
+// is the popcount of the window, taken by the sweep that also clears it for the next row.  With more
+// than one window the sub-range of each B row is found by binary search, so a product is still read
+// exactly once.
+template <int BS, bool kSorted>
 __global__ void __launch_bounds__(BS, 1)
 sym_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                   const int *__restrict__ b_rpt, const int *__restrict__ b_col,
                   const int *__restrict__ row_perm, int *__restrict__ row_cnt, int *__restrict__ bins,
-                  int bin_lo, int bin_hi, int queue, int N, int tile_cols)
+                  int bin_lo, int bin_hi, int queue, int N, int wshift, int b_vec_end)
 {
     extern __shared__ __align__(16) int smem_i[];
     unsigned *bm = reinterpret_cast<unsigned *>(smem_i);
+    uint4 *bm4 = reinterpret_cast<uint4 *>(smem_i);
     __shared__ PartScratch<BS, float> s_part;
     __shared__ int s_row, s_cnt;
     const int t = threadIdx.x;
+    const unsigned W = 1u << wshift;
+    const int nw4 = (int)(W >> 7);
+    const int nwin = (int)(((unsigned)N + W - 1u) >> wshift);
     int lo, hi;
     class_range(bins, bin_lo, bin_hi, lo, hi);
     const int n = hi - lo;
+    for (int i = t; i < nw4; i += BS) bm4[i] = make_uint4(0u, 0u, 0u, 0u);
     while (true) {
         if (t == 0) {
             s_row = atomicAdd(&bins[kBinQueue + queue], 1);
@@ -144,22 +151,22 @@ sym_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
         const int rid = row_perm[lo + r];
         const int a_beg = a_rpt[rid], a_end = a_rpt[rid + 1];
         int cnt = 0;
-        for (int t0 = 0; t0 < N; t0 += tile_cols) {
-            const int ncols = min(tile_cols, N - t0);
-            const int nw4 = (ncols + 127) >> 7;
-            uint4 *bm4 = reinterpret_cast<uint4 *>(bm);
-            for (int i = t; i < nw4; i += BS) bm4[i] = make_uint4(0u, 0u, 0u, 0u);
-            __syncthreads();
-            for_each_product_parts<BS, false, float>(
-                t, a_beg, a_end, a_col, (const float *)nullptr, b_rpt, b_col, (const float *)nullptr, s_part,
-                [&](int c, float) {
-                    const unsigned cc = (unsigned)(c - t0);
-                    if (kSingle || cc < (unsigned)ncols) {
-                        const unsigned bit = 1u << (cc & 31);
-                        unsigned *w = bm + (cc >> 5);
-                        if (!(*((volatile unsigned *)w) & bit)) cnt += !(atomicOr(w, bit) & bit);
-                    }
-                });
+        for (int win = 0; win < nwin; ++win) {
+            const int c0 = (int)((unsigned)win << wshift);
+            const int c1 = (int)min((unsigned)N, (unsigned)c0 + W);
+            for (int base = a_beg; base < a_end; base += BS) {
+                const int total = stage_parts_range<BS, false, float>(t, base, a_end, a_col, (const float *)nullptr,
+                                                                      b_rpt, b_col, c0, c1, kSorted && win > 0,
+                                                                      kSorted && win < nwin - 1, s_part);
+                run_parts_mark<BS, !kSorted, float>(t, total, b_col, b_vec_end, s_part, bm, c0, (unsigned)(c1 - c0));
+            }
+            // count and clear in one sweep (run_parts ended with a barrier)
+            for (int i = t; i < nw4; i += BS) {
+                const uint4 v = bm4[i];
+                cnt += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+                bm4[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            // the next marks are ordered after this sweep by the barriers of stage_parts_range
         }
         cnt = warp_sum(cnt);
         if ((t & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
@@ -220,7 +227,7 @@ int spgemm_symbolic(nsp_context *ctx, int M, int K, int N, const int *a_rpt, con
     sp.K = K;
     sp.N = N;
     if (plan_reserve(ctx, M) != 0) return -1;
-    if (plan_by_intprod(ctx, M, N > 0 ? N : 1, a_rpt, a_col, b_rpt) != 0) return -1;
+    if (plan_by_intprod(ctx, M, K, N > 0 ? N : 1, a_rpt, a_col, b_rpt, b_col) != 0) return -1;
 
     // ---- class ladder (symbolic shift 5: bin b holds 2^(4+b) < v <= 2^(5+b)) ----
     //   bin 0          <= 32        4 threads / row, 64 slots
@@ -228,14 +235,18 @@ int spgemm_symbolic(nsp_context *ctx, int M, int K, int N, const int *a_rpt, con
     //   bins 5..7      <= 4096      CTA(256) / row, <= 8192 slots (32 KiB)
     //   bins 8..9      <= 16384     CTA(1024) / row, <= 32768 slots (128 KiB)
     //   bins >= bm_bin              CTA(1024) / row, bitmap over column tiles
-    const int smem_cap = ctx->max_smem_optin - kStaticSmemReserve;
-    const int tile_max = (smem_cap / 16) * 128;                    // columns one bitmap tile can hold
-    const int tile_cols = N < tile_max ? ((N + 127) / 128) * 128 : tile_max;
+    // bitmap window: power of two >= N in [2^16, 2^20] columns (8 KiB .. 128 KiB of shared memory)
+    int ws_max = ctx->opt_sym_window_shift > 0 ? (int)ctx->opt_sym_window_shift : 20;
+    if (ws_max < 16) ws_max = 16;
+    if (ws_max > 20) ws_max = 20;
+    int wshift = 16;
+    while (wshift < ws_max && (1ll << wshift) < (long long)N) ++wshift;
+    const bool one_window = (1ll << wshift) >= (long long)N;
     int bm_bin = 10;
-    if (N <= tile_max) {
-        // one tile covers the row: clearing + counting the bitmap costs ~N/8 bytes of shared-memory
-        // traffic per row, the probe loop of the hash set costs per product; measured on R-MAT
-        // (scale 18/20, N = 2^18 / 2^20) the bitmap wins from ~N/512 products per row upwards
+    if (one_window) {
+        // one window covers the row: sweeping the bitmap costs ~N/8 bytes of shared-memory traffic per
+        // row, the probe loop of the hash set costs per product; measured on R-MAT (scale 18/20,
+        // N = 2^18 / 2^20) the bitmap wins from ~N/512 products per row upwards
         const int v = N / 512 + 1;
         bm_bin = log_bin(v, kSymShift) + 1;
         if (bm_bin < 5) bm_bin = 5;
@@ -250,13 +261,16 @@ int spgemm_symbolic(nsp_context *ctx, int M, int K, int N, const int *a_rpt, con
     if (M > 0) {
         // heaviest first
         if (rows_in(sp, bm_bin, kNumBins - 1) > 0) {
-            const size_t smem = (size_t)((tile_cols + 127) / 128) * 16;
+            const size_t smem = (size_t)1 << (wshift - 3);
             const int grid = imin(rows_in(sp, bm_bin, kNumBins - 1), (long long)sms);
-            auto kern = N <= tile_max ? sym_bitmap_kernel<1024, true> : sym_bitmap_kernel<1024, false>;
+            auto kern = sp.b_sorted ? sym_bitmap_kernel<1024, true> : sym_bitmap_kernel<1024, false>;
+            const int b_vec_end = ((reinterpret_cast<uintptr_t>(b_col) & 15u) != 0 || ctx->opt_no_vec)
+                                      ? 0 : (int)(sp.b_nnz & ~3ll);
             NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             prof_class(ctx, "sym_bitmap", bm_bin, kNumBins - 1);
             kern<<<grid, 1024, smem, ctx->stream>>>(a_rpt, a_col, b_rpt, b_col, sp.d_row_perm, sp.d_row_cnt,
-                                                    sp.d_bins, bm_bin, kNumBins - 1, 4, N, tile_cols);
+                                                    sp.d_bins, bm_bin, kNumBins - 1, 4, N, wshift,
+                                                    b_vec_end);
             ctx->prof_end();
             ctx->launches += 1;
             NSP_CUDA_TRY(ctx, cudaGetLastError());

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--opt", action="append", default=[], help="name=value")
     ap.add_argument("--b", default="self", help="self | er4")
     ap.add_argument("--skip-check", action="store_true")
+    ap.add_argument("--sweep", default="", help="';'-separated option sets 'k=v,k=v' run one after another")
     args = ap.parse_args()
     dt = np.float32 if args.dtype == "f32" else np.float64
     t = time.time()
@@ -35,23 +36,30 @@ def main():
     if b is not a:
         b.memcpy()
     ctx.profile(True)
-    for step in range(args.steps):
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record()
-        d_rpt64, nnz, ip = ns.spgemm_symbolic(a, b, ctx)
-        e1.record()
-        d_col, d_val = ns.spgemm_numeric(a, b, d_rpt64, nnz, ctx)
-        e2.record()
-        torch.cuda.synchronize()
-        ts, tn = e0.elapsed_time(e1), e1.elapsed_time(e2)
-        prof = ctx.profile_dump()
-        print(f"step {step}: symbolic {ts:.2f} ms numeric {tn:.2f} ms total {ts + tn:.2f} ms  "
-              f"IP={ip} nnzC={nnz}  GFLOPS={2 * ip / (ts + tn) / 1e6:.1f}", flush=True)
-        if step == args.steps - 1:
-            for n, ms, rows, kip, alen, _ in prof:
-                print(f"   {n:20s} {ms:10.3f} ms rows={rows:9d} ip={kip:13d} alen={alen:11d} "
-                      f"avgB={kip / max(alen, 1):8.1f}  Gprod/s={kip / max(ms, 1e-9) / 1e6:8.2f}")
-        del d_col, d_val, d_rpt64
+    sweeps = [x for x in args.sweep.split(";")] if args.sweep else [""]
+    for sw in sweeps:
+      if sw:
+        print(f"--- options: {sw}", flush=True)
+        for o in sw.split(","):
+            k, v = o.split("=")
+            ctx.set_option(k, int(v))
+      for step in range(args.steps):
+          e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+          e0.record()
+          d_rpt64, nnz, ip = ns.spgemm_symbolic(a, b, ctx)
+          e1.record()
+          d_col, d_val = ns.spgemm_numeric(a, b, d_rpt64, nnz, ctx)
+          e2.record()
+          torch.cuda.synchronize()
+          ts, tn = e0.elapsed_time(e1), e1.elapsed_time(e2)
+          prof = ctx.profile_dump()
+          print(f"step {step}: symbolic {ts:.2f} ms numeric {tn:.2f} ms total {ts + tn:.2f} ms  "
+                f"IP={ip} nnzC={nnz}  GFLOPS={2 * ip / (ts + tn) / 1e6:.1f}", flush=True)
+          if step == args.steps - 1:
+              for n, ms, rows, kip, alen, _ in prof:
+                  print(f"   {n:20s} {ms:10.3f} ms rows={rows:9d} ip={kip:13d} alen={alen:11d} "
+                        f"avgB={kip / max(alen, 1):8.1f}  Gprod/s={kip / max(ms, 1e-9) / 1e6:8.2f}")
+          del d_col, d_val, d_rpt64
     if args.skip_check:
         return
     # linearity check: C*1 == A*(B*1) in fp64
