@@ -4,7 +4,8 @@
 NVCC      ?= nvcc
 CXX       := /usr/bin/g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fopenmp --expt-extended-lambda -Iinclude
+# make EXTRA=-DNSP_PHASE_TIMING rebuilds the heavy numeric kernel with per-phase cycle counters
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fopenmp --expt-extended-lambda -Iinclude $(EXTRA)
 REF_DIR   ?= /root/reference
 SRC       := nsparse_b200/csrc
 OBJ       := build/obj

@@ -41,6 +41,24 @@ int nsp_set_option(nsp_context *ctx, const char *name, long long value)
     else if (!strcmp(name, "profile")) ctx->profile = value != 0;
     else if (!strcmp(name, "debug")) ctx->opt_debug = value;
     else if (!strcmp(name, "no_vec")) ctx->opt_no_vec = value;
+    else if (!strcmp(name, "num_cap")) ctx->opt_num_cap = value;
+    else if (!strcmp(name, "phase_timing")) {
+        // value 1: start accumulating; value 2: print the totals (cycles summed over CTAs) and reset
+        if (value == 2 && ctx->d_phase) {
+            long long h[12];
+            cudaDeviceSynchronize();
+            cudaMemcpy(h, ctx->d_phase, sizeof(h), cudaMemcpyDeviceToHost);
+            cudaMemset(ctx->d_phase, 0, sizeof(h));
+            static const char *nm[12] = {"row+clear", "mark stage", "mark run", "rank", "scan+bounds", "emit", "copy cols",
+                                         "chunk stage", "value run", "copy vals", "red mode", "-"};
+            long long tot = 0;
+            for (int i = 0; i < 12; ++i) tot += h[i];
+            for (int i = 0; i < 11; ++i)
+                printf("   phase %-12s %8.3f Mcyc/CTA  %5.1f%%\n", nm[i], h[i] / 1e6 / ctx->sm_count, 100.0 * h[i] / (tot ? tot : 1));
+            fflush(stdout);
+        }
+        ctx->opt_phase_timing = value != 0;
+    }
     else if (!strcmp(name, "sym_window_shift")) ctx->opt_sym_window_shift = value;
     else if (!strcmp(name, "num_window_shift")) ctx->opt_num_window_shift = value;
     else if (!strcmp(name, "lanes_per_brow")) {

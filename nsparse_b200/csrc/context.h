@@ -66,7 +66,18 @@ struct nsp_context {
     long long opt_num_bitmap_min = -1;   // rows with nnz(C_i)  >  this go to the bitmap-rank kernel
     long long opt_sym_window_shift = 0;  // log2 of the symbolic bitmap window (0: default 20)
     long long opt_num_window_shift = 0;  // log2 of the numeric bitmap window (0: default 19)
+    long long opt_num_cap = 0;           // > 0: upper limit of the accumulator chunk (tests)
     long long opt_no_vec = 0;            // 1: never read B.col with 128-bit loads (tests)
+    long long opt_phase_timing = 0;      // 1: the heavy numeric kernel accumulates cycles per phase (development)
+    long long *d_phase = nullptr;
+    long long *phase_cycles()
+    {
+        if (!d_phase) {
+            cudaMalloc((void **)&d_phase, 12 * sizeof(long long));
+            cudaMemset(d_phase, 0, 12 * sizeof(long long));
+        }
+        return d_phase;
+    }
     long long opt_debug = 0;             // development only: bit 0 skip emit, 1 skip value pass, 2 skip zero-fill
     long long opt_lanes_per_brow = 0;    // 0: pick from nnz(B)/K
 

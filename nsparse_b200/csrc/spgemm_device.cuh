@@ -55,9 +55,15 @@ __device__ __forceinline__ int group_inclusive_scan(int v, int t, int *wtot)
         const int wid = t >> 5;
         if (lane == 31) wtot[wid] = inc;
         __syncthreads();
-        int add = 0;
-        for (int w = 0; w < wid; ++w) add += wtot[w];
-        inc += add;
+        // every warp scans the (at most 32) warp totals itself: no serial loop, no second barrier
+        int w = lane < GROUP / 32 ? wtot[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += x;
+        }
+        const int before = __shfl_sync(0xffffffffu, w, (wid + 31) & 31);
+        inc += wid > 0 ? before : 0;
     }
     return inc;
 }
@@ -412,17 +418,18 @@ __device__ __forceinline__ void run_parts(int t, int total, const int *__restric
 // ---------------------------------------------------------------------------------------------
 // Column bitmap of the heavy kernels: plain bit order (column cc of the window is bit cc & 31 of
 // 32-bit word cc >> 5); the 64-bit word PAIRS are swizzled inside every batch of 32 pairs (2048
-// columns): pair j of batch b lives at j ^ h(b), h(b) = (b ^ (b >> 5)) & 31.  Graph generators such as
+// columns): pair j of batch b lives at j ^ (b & 31).  Graph generators such as
 // R-MAT make every bit of a column index 0 with probability ~0.76, so a quarter of ALL products share
 // any given 5-bit field of the column index and would hit one bank (measured: 14 wavefronts per
-// shared-memory atomic instead of ~3); after the swizzle the bank depends on the column bits 6..20.
+// shared-memory atomic instead of ~3); after the swizzle the bank depends on the column bits 6..15
+// (one fold: two instructions per address -- the kernels are issue-bound).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned bitmap_swz(unsigned batch) { return (batch ^ (batch >> 5)) & 31u; }
+__device__ __forceinline__ unsigned bitmap_swz(unsigned batch) { return batch & 31u; }
 
 // physical index of logical 32-bit word w32 (= cc >> 5)
 __device__ __forceinline__ unsigned bitmap_word32(unsigned w32)
 {
-    return w32 ^ (((w32 >> 5) ^ (w32 >> 10)) & 0x3eu);
+    return w32 ^ ((w32 >> 5) & 0x3eu);
 }
 
 // Mark pass over the staged parts.  Every lane reads FOUR CONSECUTIVE products per 128-bit load (two
@@ -500,6 +507,13 @@ __device__ __forceinline__ void run_parts_mark(int t, int total, const int *__re
     __syncthreads();
 }
 
+// Accumulator index swizzle.  On a dense row of C the rank of a column is (nearly) the column itself,
+// so the ranks inherit the bit skew of the column indices: a quarter of the shared-memory CAS of a warp
+// hit one bank (measured 16-22 wavefronts per ATOMS.CAST instead of ~5).  XOR-ing the next five index
+// bits into the bank bits is a permutation inside every aligned group of 32 accumulators, so the
+// copy-out stays conflict free.
+__device__ __forceinline__ int acc_swz(int i) { return i ^ ((i >> 5) & 31); }
+
 // ---------------------------------------------------------------------------------------------
 // Open-addressing insert, linear probing, key-only (symbolic).  Returns 1 if the key was new.
 // Same scheme as the reference probe loop (kernel_spgemm_hash_d.cu:299-317) but the table is
@@ -507,7 +521,7 @@ __device__ __forceinline__ void run_parts_mark(int t, int total, const int *__re
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int hash_insert_key(int *tab, unsigned mask, int col)
 {
-    unsigned h = hash_col(col) & mask;
+    unsigned h = hash_slot(col, mask);
     while (true) {
         const int k = *((volatile int *)(tab + h));
         if (k == col) return 0;
@@ -524,7 +538,7 @@ __device__ __forceinline__ int hash_insert_key(int *tab, unsigned mask, int col)
 template <typename real>
 __device__ __forceinline__ void hash_accumulate(int *keys, real *vals, unsigned mask, int col, real v)
 {
-    unsigned h = hash_col(col) & mask;
+    unsigned h = hash_slot(col, mask);
     while (true) {
         const int k = *((volatile int *)(keys + h));
         if (k == col) break;

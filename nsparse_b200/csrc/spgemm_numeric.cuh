@@ -156,7 +156,7 @@ num_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
 // Every product is read once per pass whatever the number of windows and chunks: the sub-range of each
 // B row that falls into a column range is found by searching the sorted B row (stage_window /
 // stage_chunk keep a cursor per entry; rows with more than 1024 entries search from scratch).
-// Shared memory: W/8 bitmap + W/16 prefixes + cap * max(4, sizeof(real)) staging / accumulators.
+// Shared memory: W/8 bitmap + W/16 prefixes + cap * (sizeof(real) + 4) accumulators and columns.
 constexpr int kMaxChunks = 512;
 constexpr int kMaxBatches = 256;            // W <= 2^19: 2048 columns per batch
 
@@ -177,13 +177,32 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                   const int *__restrict__ b_col, const real *__restrict__ b_val,
                   const long long *__restrict__ c_rpt, int *__restrict__ c_col, real *__restrict__ c_val,
                   const int *__restrict__ row_perm, int *__restrict__ bins, int bin_lo, int bin_hi,
-                  int queue, int N, int wshift, int cap, int b_vec_end, int dbg)
+                  int queue, int N, int wshift, int cap, int b_vec_end, int dbg, long long *phase_cycles)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = BS / 32;
     static_assert(NW == 32, "the batch scan and the entry search assume 32 warps");
+    // development aid (build with -DNSP_PHASE_TIMING, nsp_set_option "phase_timing"): thread 0 charges the
+    // cycles between barriers to twelve phases and adds them to phase_cycles[] at the end
+#ifdef NSP_PHASE_TIMING
+    long long ph_last = 0;
+    long long ph_acc[12];
+    if (phase_cycles) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) ph_acc[i] = 0;
+        ph_last = clock64();
+    }
+#define PH(i)                                              \
+    if (phase_cycles && threadIdx.x == 0) {                \
+        const long long now = clock64();                   \
+        ph_acc[i] += now - ph_last;                        \
+        ph_last = now;                                     \
+    }
+#else
+#define PH(i)
+#endif
     __shared__ PartScratch<BS, real> s_part;
-    __shared__ int s_row, s_next;
+    __shared__ int s_row;
     __shared__ int s_batch[kMaxBatches + 1];    // outputs before the batch (exclusive), window relative
     __shared__ int s_bound[kMaxChunks + 1];
     const unsigned W = 1u << wshift;
@@ -193,7 +212,7 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
     unsigned *pre2 = reinterpret_cast<unsigned *>(smem_raw + (W >> 3));            // per pair: two 16-bit prefixes
     const unsigned short *pre16 = reinterpret_cast<const unsigned short *>(pre2);  // the same per 32-bit word
     real *acc = reinterpret_cast<real *>(smem_raw + (W >> 3) + (W >> 4));
-    int *stg = reinterpret_cast<int *>(acc);    // column staging aliases the accumulators
+    int *cols = reinterpret_cast<int *>(acc + cap);
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     int lo, hi;
     class_range(bins, bin_lo, bin_hi, lo, hi);
@@ -219,47 +238,79 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                 for (int i = t; i < (int)(W >> 7); i += BS) bm4[i] = make_uint4(0u, 0u, 0u, 0u);
             }
             __syncthreads();
+            PH(0);
             // ---- mark ----
             int staged_total = 0;
             const unsigned ncols = (unsigned)(c1 - c0);
             if (one_slab) {
                 staged_total = stage_window<BS, true, real>(t, a_beg, E, glog, a_col, a_val, b_rpt, b_col, c1,
                                                             win == 0 || !kSorted, cut_hi, s_part);
+                PH(1);
                 run_parts_mark<BS, !kSorted, real>(t, staged_total, b_col, b_vec_end, s_part, bm32, c0, ncols);
+                PH(2);
             } else {
                 for (int base = a_beg; base < a_end; base += BS) {
                     const int total = stage_parts_range<BS, false, real>(t, base, a_end, a_col, a_val, b_rpt, b_col, c0,
                                                                          c1, cut_lo, cut_hi, s_part);
                     run_parts_mark<BS, !kSorted, real>(t, total, b_col, b_vec_end, s_part, bm32, c0, ncols);
+                    PH(2);
                 }
             }
-            // ---- rank: per-word prefixes inside every batch, batch totals, CTA-wide exclusive scan ----
-            for (int b = wid; b < nbatch; b += NW) {
-                const unsigned pj = (unsigned)(b << 5) | ((unsigned)lane ^ bitmap_swz((unsigned)b));
-                const uint2 wd = bm64[pj];
-                const int cl = __popc(wd.x);
-                const int c = cl + __popc(wd.y);
-                int inc = c;
+            // ---- rank: per-word prefixes inside every batch (four batches in flight per warp: the scan is
+            //      a chain of five dependent shuffles), batch totals, exclusive scan of the totals by warp 0 ----
+            for (int b0 = wid * 4; b0 < nbatch; b0 += NW * 4) {
+                unsigned pj[4];
+                int cl[4], c[4], inc[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    pj[u] = (unsigned)((b0 + u) << 5) | ((unsigned)lane ^ bitmap_swz((unsigned)(b0 + u)));
+                    const uint2 wd = bm64[pj[u]];
+                    cl[u] = __popc(wd.x);
+                    c[u] = cl[u] + __popc(wd.y);
+                    inc[u] = c[u];
+                }
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += v;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int v = __shfl_up_sync(0xffffffffu, inc[u], o);
+                        if (lane >= o) inc[u] += v;
+                    }
                 }
-                const unsigned ex = (unsigned)(inc - c);
-                pre2[pj] = ex | ((ex + (unsigned)cl) << 16);
-                if (lane == 31) s_batch[b] = inc;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned ex = (unsigned)(inc[u] - c[u]);
+                    pre2[pj[u]] = ex | ((ex + (unsigned)cl[u]) << 16);
+                    if (lane == 31) s_batch[b0 + u] = inc[u];
+                }
             }
             __syncthreads();
-            int tile_nnz;
-            {
-                const int v = t < nbatch ? s_batch[t] : 0;
-                const int inc = group_inclusive_scan<BS>(v, t, s_part.wtot);
-                __syncthreads();                       // everyone has read its count and the warp totals
-                if (t < nbatch) s_batch[t] = inc - v;
-                if (t == BS - 1) s_batch[nbatch] = inc;
-                __syncthreads();
-                tile_nnz = s_batch[nbatch];
+            PH(3);
+            if (wid == 0) {
+                // nbatch <= 256: lane l owns the batches 8l .. 8l+7 (nbatch is a multiple of 32)
+                const int per = nbatch >> 5;
+                int v[8], sum = 0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    v[u] = u < per ? s_batch[lane * per + u] : 0;
+                    sum += v[u];
+                }
+                int inc = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int x = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += x;
+                }
+                int run = inc - sum;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (u < per) s_batch[lane * per + u] = run;
+                    run += v[u];
+                }
+                if (lane == 31) s_batch[nbatch] = inc;
             }
+            __syncthreads();
+            const int tile_nnz = s_batch[nbatch];
             const int nch = (tile_nnz + cap - 1) / cap;
             // chunk boundary columns: chunk k starts at the column of rank k * cap (one warp per boundary)
             for (int k = 1 + wid; k < nch; k += NW) {
@@ -279,59 +330,21 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                     s_bound[k] = c0 + (((b << 5) + lane) << 6) + colw;
                 }
             }
-            if (t == 0) s_next = 0;
             __syncthreads();
-            // ---- chunk by chunk: columns, then values ----
-            for (int k = 0; k < nch; ++k) {
+            PH(4);
+            // ---- chunk by chunk ----
+            // Rows whose A entries fit one slab: acc[0..cnt) is zeroed, every product of the chunk's column
+            // range is added at acc[rank - chunk base] with a shared-memory atomic and stores its column at
+            // cols[rank - chunk base] (a plain store: every writer of a slot writes the same value), then both
+            // arrays go to C.val / C.col with coalesced stores.  Emitting the columns here costs two
+            // instructions per product with all lanes busy; walking the set bits of the bitmap instead cost
+            // 24 % of the kernel's instructions at 3-4 active lanes (profiles/r1_ncu_bitmap_s20_v4.txt).
+            for (int k = 0; k < nch && one_slab && !(dbg & 2); ++k) {
                 const int r0 = k * cap;
                 const int cnt = min(tile_nnz - r0, cap);
                 const int col_lo = k > 0 ? s_bound[k] : c0;
                 const int col_hi = k < nch - 1 ? s_bound[k + 1] : c1;
-                if (!(dbg & 1)) {
-                    // Batches are CLAIMED: a skewed row keeps its dense batches where the batch index has
-                    // few one bits, and any static deal by batch index inherits that skew.
-                    while (true) {
-                        int b = 0;
-                        if (lane == 0) b = atomicAdd(&s_next, 1);
-                        b = __shfl_sync(0xffffffffu, b, 0);
-                        if (b >= nbatch) break;
-                        const int base = s_batch[b] - r0;
-                        const int bend = s_batch[b + 1] - r0;
-                        if (bend <= 0 || base >= cnt || bend == base) continue;      // no output of this chunk
-                        const unsigned pj = (unsigned)(b << 5) | ((unsigned)lane ^ bitmap_swz((unsigned)b));
-                        uint2 wd = bm64[pj];
-                        int pos = base + (int)(pre2[pj] & 0xffffu);
-                        const int cbase = c0 + (((b << 5) + lane) << 6);
-                        if (base >= 0 && bend <= cnt) {
-                            while (wd.x) {
-                                stg[pos++] = cbase + __ffs((int)wd.x) - 1;
-                                wd.x &= wd.x - 1;
-                            }
-                            while (wd.y) {
-                                stg[pos++] = cbase + 31 + __ffs((int)wd.y);
-                                wd.y &= wd.y - 1;
-                            }
-                        } else {                                   // batch straddles a chunk boundary
-                            while (wd.x) {
-                                if ((unsigned)pos < (unsigned)cnt) stg[pos] = cbase + __ffs((int)wd.x) - 1;
-                                ++pos;
-                                wd.x &= wd.x - 1;
-                            }
-                            while (wd.y) {
-                                if ((unsigned)pos < (unsigned)cnt) stg[pos] = cbase + 31 + __ffs((int)wd.y);
-                                ++pos;
-                                wd.y &= wd.y - 1;
-                            }
-                        }
-                    }
-                    __syncthreads();
-                    if (t == 0) s_next = 0;
-                    int *cc = c_col + out + r0;
-                    for (int i = t; i < cnt; i += BS) cc[i] = stg[i];
-                    __syncthreads();
-                }
-                if (dbg & 2) continue;
-                for (int i = t; i < cnt; i += BS) acc[i] = real(0);
+                for (int i = t; i < ((cnt + 31) & ~31); i += BS) acc[i] = real(0);   // whole swizzle groups
                 // (the barriers of the staging below order the zeroes before the adds)
                 auto add = [&](int c, real v) {
                     if (!kSorted && (unsigned)(c - col_lo) >= (unsigned)(col_hi - col_lo)) return;
@@ -340,30 +353,93 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                     const unsigned p32 = bitmap_word32(w32);
                     const int rank = s_batch[w32 >> 6] + (int)pre16[p32] +
                                      __popc(bm32[p32] & ((1u << (cc & 31u)) - 1u));
-                    atomicAdd(acc + (rank - r0), v);
+                    const int idx = acc_swz(rank - r0);
+                    cols[idx] = c;
+                    atomicAdd(acc + idx, v);
                 };
-                if (one_slab) {
-                    int total = staged_total;              // one chunk (or unsorted B): the mark pass staged it
-                    if (kSorted && nch > 1)
-                        total = stage_chunk<BS, real>(t, E, glog, b_col, col_hi, k == nch - 1, s_part);
-                    else
-                        __syncthreads();
-                    run_parts<BS, true, real>(t, total, b_col, b_val, s_part, add);
-                } else {
-                    for (int base = a_beg; base < a_end; base += BS) {
-                        const int total = stage_parts_range<BS, true, real>(
-                            t, base, a_end, a_col, a_val, b_rpt, b_col, col_lo, col_hi, kSorted && (cut_lo || k > 0),
-                            kSorted && (cut_hi || k < nch - 1), s_part);
-                        run_parts<BS, true, real>(t, total, b_col, b_val, s_part, add);
-                    }
-                }
+                int total = staged_total;                  // one chunk (or unsorted B): the mark pass staged it
+                if (kSorted && nch > 1)
+                    total = stage_chunk<BS, real>(t, E, glog, b_col, col_hi, k == nch - 1, s_part);
+                else
+                    __syncthreads();
+                PH(7);
+                run_parts<BS, true, real>(t, total, b_col, b_val, s_part, add);
+                PH(8);
                 real *cv = c_val + out + r0;
-                for (int i = t; i < cnt; i += BS) cv[i] = acc[i];
-                __syncthreads();                       // the next chunk's columns reuse the buffer
+                int *cc = c_col + out + r0;
+                for (int i = t; i < cnt; i += BS) {
+                    const int j = acc_swz(i);
+                    cv[i] = acc[j];
+                    cc[i] = cols[j];
+                }
+                __syncthreads();                       // the next chunk reuses the buffers
+                PH(9);
+            }
+            // Rows with more than BS entries of A (0.1 % of the rows, a seventh of the products on R-MAT)
+            // would re-search every slab for every chunk: they emit their columns from the bitmap, chunk by
+            // chunk through the cols buffer, and add their values straight into C.val with red.global in
+            // ONE pass over the products.
+            if (!one_slab) {
+                for (int k = 0; k < nch && !(dbg & 1); ++k) {
+                    const int r0 = k * cap;
+                    const int cnt = min(tile_nnz - r0, cap);
+                    for (int step = 0; step < (nbatch >> 5); ++step) {
+                        const int b = (step << 5) | ((wid + 11 * step) & 31);
+                        const int base = s_batch[b] - r0;
+                        const int bend = s_batch[b + 1] - r0;
+                        if (bend <= 0 || base >= cnt || bend == base) continue;      // no output of this chunk
+                        const unsigned pj = (unsigned)(b << 5) | ((unsigned)lane ^ bitmap_swz((unsigned)b));
+                        uint2 wd = bm64[pj];
+                        int pos = base + (int)(pre2[pj] & 0xffffu);
+                        const int cbase = c0 + (((b << 5) + lane) << 6);
+                        while (wd.x) {
+                            if ((unsigned)pos < (unsigned)cnt) cols[pos] = cbase + __ffs((int)wd.x) - 1;
+                            ++pos;
+                            wd.x &= wd.x - 1;
+                        }
+                        while (wd.y) {
+                            if ((unsigned)pos < (unsigned)cnt) cols[pos] = cbase + 31 + __ffs((int)wd.y);
+                            ++pos;
+                            wd.y &= wd.y - 1;
+                        }
+                    }
+                    __syncthreads();
+                    int *cc = c_col + out + r0;
+                    for (int i = t; i < cnt; i += BS) cc[i] = cols[i];
+                    __syncthreads();
+                }
+                PH(6);
+            }
+            if (!one_slab && !(dbg & 2)) {
+                real *cv = c_val + out;
+                for (int i = t; i < tile_nnz; i += BS) cv[i] = real(0);
+                auto add_red = [&](int c, real v) {
+                    const unsigned cc = (unsigned)(c - c0);
+                    if (!kSorted && cc >= ncols) return;
+                    const unsigned w32 = cc >> 5;
+                    const unsigned p32 = bitmap_word32(w32);
+                    const int rank = s_batch[w32 >> 6] + (int)pre16[p32] +
+                                     __popc(bm32[p32] & ((1u << (cc & 31u)) - 1u));
+                    atomicAdd(cv + rank, v);
+                };
+                for (int base = a_beg; base < a_end; base += BS) {
+                    // (the barriers of the staging order the zero fill before the adds)
+                    const int total = stage_parts_range<BS, true, real>(t, base, a_end, a_col, a_val, b_rpt, b_col, c0, c1,
+                                                                        cut_lo, cut_hi, s_part);
+                    run_parts<BS, true, real>(t, total, b_col, b_val, s_part, add_red);
+                    PH(10);
+                }
             }
             out += tile_nnz;
         }
     }
+#ifdef NSP_PHASE_TIMING
+    if (phase_cycles && threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) atomicAdd((unsigned long long *)phase_cycles + i, (unsigned long long)ph_acc[i]);
+    }
+#endif
+#undef PH
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -445,20 +521,15 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
     int wshift = 16;
     while (wshift < ws_max && (1ll << wshift) < (long long)N) ++wshift;
     const size_t fixed = ((size_t)3 << wshift) / 16;
-    int cap = (int)((smem_cap - (long long)fixed) / (long long)sizeof(real));
+    int cap = (int)((smem_cap - (long long)fixed) / (long long)(sizeof(real) + sizeof(int)));
+    if (ctx->opt_num_cap > 0 && ctx->opt_num_cap < cap) cap = (int)ctx->opt_num_cap;   // tests: force many chunks
     cap &= ~127;
-    if (cap > 32768) cap = 32768;
-    const bool one_window = (1ll << wshift) >= (long long)N;
+    // Class boundary.  A bitmap row costs a sweep per window whatever its size (~10 us), a hash row a
+    // bitonic sort of its table (n log^2 n): measured on R-MAT scale 20 (two windows) the bitmap wins above
+    // ~2048 entries.  With many windows (very wide C) the hash ladder keeps everything it can hold.
+    const long long nwin_host = ((long long)N + (1ll << wshift) - 1) >> wshift;
     const int slot_bytes = 4 + (int)sizeof(real);
-    int bm_bin = 10;
-    if (one_window) {
-        // single window: bitmap + rank needs no sort, the hash path pays an O(n log^2 n) bitonic sort
-        // per row; measured crossover on R-MAT ~N/1024 entries per row
-        const int v = N / 1024 + 1;
-        bm_bin = log_bin(v, kNumShift) + 1;
-        if (bm_bin < 5) bm_bin = 5;
-        if (bm_bin > 10) bm_bin = 10;
-    }
+    int bm_bin = nwin_host <= 4 ? 8 : 10;
     if (ctx->opt_num_bitmap_min >= 0) {
         bm_bin = log_bin(num_imin(ctx->opt_num_bitmap_min, 0x7fffffff), kNumShift) + 1;
         if (bm_bin < 1) bm_bin = 1;
@@ -466,15 +537,16 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
     }
     const int sms = ctx->sm_count;
     if (num_rows_in(sp, bm_bin, kNumBins - 1) > 0) {
-        if (cap < 1024 || ((1ll << wshift) + cap - 1) / cap > kMaxChunks)
+        if (cap < 128 || ((1ll << wshift) + cap - 1) / cap > kMaxChunks)
             return ctx->fail(-4, "nsp_spgemm_numeric: shared memory too small for the bitmap kernel");
-        const size_t smem = fixed + (size_t)cap * sizeof(real);
+        const size_t smem = fixed + (size_t)cap * (sizeof(real) + sizeof(int));
         const int grid = num_imin(num_rows_in(sp, bm_bin, kNumBins - 1), (long long)sms);
         auto kern = sp.b_sorted ? num_bitmap_kernel<real, 1024, true> : num_bitmap_kernel<real, 1024, false>;
         NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         num_prof_class(ctx, "num_bitmap", bm_bin, kNumBins - 1);
         kern<<<grid, 1024, smem, ctx->stream>>>(NSP_NUM_ARGS, bm_bin, kNumBins - 1, 4, N, wshift, cap,
-                                                b_vec_end_of(ctx, b_col), (int)ctx->opt_debug);
+                                                b_vec_end_of(ctx, b_col), (int)ctx->opt_debug,
+                                                ctx->opt_phase_timing ? ctx->phase_cycles() : nullptr);
         ctx->prof_end();
         ctx->launches += 1;
         NSP_CUDA_TRY(ctx, cudaGetLastError());

@@ -241,17 +241,11 @@ int spgemm_symbolic(nsp_context *ctx, int M, int K, int N, const int *a_rpt, con
     if (ws_max > 20) ws_max = 20;
     int wshift = 16;
     while (wshift < ws_max && (1ll << wshift) < (long long)N) ++wshift;
-    const bool one_window = (1ll << wshift) >= (long long)N;
-    int bm_bin = 10;
-    if (one_window) {
-        // one window covers the row: sweeping the bitmap costs ~N/8 bytes of shared-memory traffic per
-        // row, the probe loop of the hash set costs per product; measured on R-MAT (scale 18/20,
-        // N = 2^18 / 2^20) the bitmap wins from ~N/512 products per row upwards
-        const int v = N / 512 + 1;
-        bm_bin = log_bin(v, kSymShift) + 1;
-        if (bm_bin < 5) bm_bin = 5;
-        if (bm_bin > 10) bm_bin = 10;
-    }
+    // Class boundary: a bitmap row costs a clear + count sweep per window (~4 us at 2^20 columns), the
+    // hash set costs per product; measured on R-MAT scale 20 the bitmap wins above ~4096 products per row.
+    // With many windows (very wide C) the hash ladder keeps everything it can hold (16384 products).
+    const long long nwin_host = ((long long)N + (1ll << wshift) - 1) >> wshift;
+    int bm_bin = nwin_host <= 4 ? 8 : 10;
     if (ctx->opt_sym_bitmap_min >= 0) {
         bm_bin = log_bin(imin(ctx->opt_sym_bitmap_min, 0x7fffffff), kSymShift) + 1;
         if (bm_bin < 1) bm_bin = 1;

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--opt", action="append", default=[], help="name=value")
     ap.add_argument("--b", default="self", help="self | er4")
     ap.add_argument("--skip-check", action="store_true")
+    ap.add_argument("--phases", action="store_true", help="print the cycles per phase of the heavy numeric kernel")
     ap.add_argument("--sweep", default="", help="';'-separated option sets 'k=v,k=v' run one after another")
     args = ap.parse_args()
     dt = np.float32 if args.dtype == "f32" else np.float64
@@ -43,6 +44,9 @@ def main():
         for o in sw.split(","):
             k, v = o.split("=")
             ctx.set_option(k, int(v))
+      if args.phases:
+          ctx.set_option("phase_timing", 2)
+          ctx.set_option("phase_timing", 1)
       for step in range(args.steps):
           e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
           e0.record()
@@ -56,6 +60,8 @@ def main():
           print(f"step {step}: symbolic {ts:.2f} ms numeric {tn:.2f} ms total {ts + tn:.2f} ms  "
                 f"IP={ip} nnzC={nnz}  GFLOPS={2 * ip / (ts + tn) / 1e6:.1f}", flush=True)
           if step == args.steps - 1:
+              if args.phases:
+                  ctx.set_option("phase_timing", 2)
               for n, ms, rows, kip, alen, _ in prof:
                   print(f"   {n:20s} {ms:10.3f} ms rows={rows:9d} ip={kip:13d} alen={alen:11d} "
                         f"avgB={kip / max(alen, 1):8.1f}  Gprod/s={kip / max(ms, 1e-9) / 1e6:8.2f}")

@@ -213,6 +213,71 @@ def test_wide_matrix_multi_tile_bitmap(ns):
     c2.close()
 
 
+def _heavy_case(ns, dtype, n=200_000, seed=7, unsorted=False):
+    """A few rows of every kind the heavy (bitmap) class distinguishes: a long-B-row product with tens of
+    thousands of outputs, a row with more than 1024 entries of A (several slabs), a light row."""
+    rng = np.random.default_rng(seed)
+    k = 4000
+    blen = rng.integers(1, 60, size=k)
+    blen[:40] = rng.integers(2000, 6000, size=40)          # hub rows of B
+    rpt = np.zeros(k + 1, np.int64)
+    rpt[1:] = np.cumsum(blen)
+    bcol = np.concatenate([np.sort(rng.choice(n, size=int(l), replace=False)) for l in blen]).astype(np.int32)
+    # a dense run so that consecutive columns share bitmap words
+    bcol[rpt[3]:rpt[3] + 1500] = np.arange(1000, 2500)
+    bcol[rpt[3]:rpt[4]] = np.unique(np.concatenate([bcol[rpt[3]:rpt[3] + 1500],
+                                                    rng.choice(np.arange(3000, n), size=int(blen[3]) - 1500,
+                                                               replace=False)]))[:blen[3]]
+    bval = rng.integers(1, 4, size=int(rpt[-1])).astype(dtype)
+    if unsorted:
+        for i in range(k):
+            p = rng.permutation(int(blen[i]))
+            bcol[rpt[i]:rpt[i + 1]] = bcol[rpt[i]:rpt[i + 1]][p]
+    b = ns.CSR(k, n, rpt.astype(np.int32), bcol, bval)
+    rows = [np.sort(rng.choice(40, size=30, replace=False)),                 # 30 hub rows: ~100 k products
+            np.sort(rng.choice(k, size=2500, replace=False)),                # 2500 entries: three slabs
+            np.sort(rng.choice(np.arange(40, k), size=5, replace=False)),    # light
+            np.array([3]),                                                    # the dense-run row alone
+            np.sort(rng.choice(k, size=1024, replace=False))]                # exactly one slab
+    arpt = np.zeros(len(rows) + 1, np.int64)
+    arpt[1:] = np.cumsum([len(r) for r in rows])
+    a = ns.CSR(len(rows), k, arpt.astype(np.int32), np.concatenate(rows).astype(np.int32),
+               rng.integers(1, 3, size=int(arpt[-1])).astype(dtype))
+    return a, b
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("opts", [
+    {},                                                            # default windows / chunk size
+    {"num_cap": 1024, "num_bitmap_min": 16, "sym_bitmap_min": 32},  # dozens of chunks per row
+    {"num_window_shift": 16, "sym_window_shift": 16, "num_bitmap_min": 16, "sym_bitmap_min": 32},   # 4 windows
+    {"num_window_shift": 16, "sym_window_shift": 16, "num_cap": 256, "no_vec": 1, "num_bitmap_min": 16,
+     "sym_bitmap_min": 32},                                        # windows x chunks, scalar mark loads
+])
+def test_heavy_class_windows_chunks_slabs(ns, dtype, opts):
+    """Every path of the bitmap kernels: column windows, accumulator chunks (cursor search), rows with more
+    than 1024 A entries (red.global mode), dense runs, the scalar fallback of the 128-bit mark loads."""
+    a, b = _heavy_case(ns, dtype)
+    c2 = ns.Context(0)
+    for k, v in opts.items():
+        c2.set_option(k, v)
+    _check(ns, c2, a, b, exact_values=True)
+    c2.close()
+
+
+@pytest.mark.parametrize("opts", [{}, {"num_cap": 512, "num_window_shift": 16, "sym_window_shift": 16,
+                                       "num_bitmap_min": 16, "sym_bitmap_min": 32}])
+def test_heavy_class_unsorted_b(ns, opts):
+    """Rows of B not column-sorted (reader of symmetric files, nsparse.cu:115-123): the kernels detect it
+    and filter by column range instead of searching."""
+    a, b = _heavy_case(ns, np.float64, unsorted=True)
+    c2 = ns.Context(0)
+    for k, v in opts.items():
+        c2.set_option(k, v)
+    _check(ns, c2, a, b, exact_values=True)
+    c2.close()
+
+
 def test_rpt32_narrowing_and_overflow_guard(ns, ctx):
     import ctypes as C
 
