@@ -1,0 +1,129 @@
+"""GPU tests shaped like the BASELINE.json configs beyond the bench line.
+
+  C2 (R-MAT scale 20, A^2, fp32) at FULL size through size-independent properties: the golden counts of
+     the deterministic generator, ascending columns in every row, and linearity  C*1 == A*(B*1).
+  C4 (R-MAT x uniform-random B, fp64) and C5 (power-law A with a 64 K-entry row, very wide B, fp64) at
+     reduced size against the CPU oracle, bit-exact (integer-valued inputs make every sum exact).
+  f1: the numeric phase re-run with new values on an unchanged pattern.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ns():
+    import nsparse_b200 as ns
+
+    ns.load_library()
+    return ns
+
+
+def _check(ns, ctx, a, b):
+    a.memcpy()
+    b.memcpy()
+    c = ns.spgemm_kernel_hash(a, b, ctx)
+    ctx.sync()
+    got = c.to_host()
+    want = oracle.spgemm(a.rpt, a.col, a.val, b.rpt, b.col, b.val, acc_double=True, n_cols=b.N)
+    assert c.nnz == int(want[0][-1])
+    ok, msg = oracle.check_spgemm_answer(got, want)
+    assert ok, msg
+    assert np.array_equal(got[2], want[2])
+    return c
+
+
+def test_c4_reduced_rmat_times_uniform_fp64(ns):
+    from nsparse_b200 import gen
+
+    a = gen.rmat_csr(16, 32, seed=12345, dtype=np.float64, values="small_int")
+    b = gen.er_csr(a.N, a.N, 4, seed=54321, dtype=np.float64, values="ones")
+    ctx = ns.Context(0)
+    _check(ns, ctx, a, b)
+    ctx.close()
+
+
+def test_c5_reduced_powerlaw_overflow_rows_fp64(ns):
+    """max row 64 K entries x 4 nnz per B row = 262 144 products in one row, C four numeric bitmap windows
+    wide: the rows above the shared-memory hash ladder take windows x chunks, the 64 K-entry row the
+    multi-slab path."""
+    from nsparse_b200 import gen
+
+    n = 1 << 17
+    a = gen.powerlaw_csr(n, mean_nnz=48, max_row=65536, seed=777, dtype=np.float64, values="ones")
+    assert a.nnz_max == 65536
+    b = gen.er_csr(n, 1 << 21, 4, seed=54321, dtype=np.float64, values="ones")
+    ctx = ns.Context(0)
+    c = _check(ns, ctx, a, b)
+    assert c.nnz > 3 * a.nnz
+    ctx.close()
+
+
+def test_c2_full_size_properties(ns):
+    """Config C2 itself: 2.09e10 intermediate products, 9.7e9 output entries (int64 row pointer)."""
+    import torch
+
+    from nsparse_b200 import gen
+
+    a = gen.rmat_csr(20, 16, seed=12345, dtype=np.float32)
+    assert (a.M, a.nnz) == (1 << 20, 16085138)
+    a.memcpy()
+    ctx = ns.Context(0)
+    c = ns.spgemm_kernel_hash(a, a, ctx)
+    ctx.sync()
+    assert c.intprod == 20920190116            # get_spgemm_flop / 2 of this generator + seed
+    assert c.nnz == 9711052746                 # pinned by the first correct version of this library
+    rpt = c.d_rpt64
+    assert int(rpt[0]) == 0 and int(rpt[-1]) == c.nnz and bool((rpt[1:] >= rpt[:-1]).all())
+    # every row strictly ascending in column; C*1 accumulated per row in fp64
+    step = 1 << 28
+    rowsum = torch.zeros(a.M, dtype=torch.float64, device="cuda")
+    bad = 0
+    for s in range(0, c.nnz, step):
+        e = min(c.nnz, s + step)
+        idx = torch.arange(s, e, device="cuda")
+        row = torch.searchsorted(rpt, idx, right=True) - 1
+        col = c.d_col[s:e]
+        first = idx == rpt[row]
+        if s > 0:
+            prev = torch.cat([c.d_col[s - 1:s], col[:-1]])
+        else:
+            prev = torch.cat([col[:1] - 1, col[:-1]])
+        bad += int(((col <= prev) & ~first).sum())
+        assert int(col.min()) >= 0 and int(col.max()) < a.N
+        rowsum.index_add_(0, row, c.d_val[s:e].double())
+        del idx, row, col, first, prev
+    assert bad == 0
+    arow = torch.repeat_interleave(torch.arange(a.M, device="cuda"), (a.d_rpt[1:] - a.d_rpt[:-1]).long())
+    b1 = torch.zeros(a.M, dtype=torch.float64, device="cuda").index_add_(0, arow, a.d_val.double())
+    ab1 = torch.zeros(a.M, dtype=torch.float64, device="cuda").index_add_(0, arow, a.d_val.double() * b1[a.d_col.long()])
+    rel = ((rowsum - ab1).abs() / ab1.abs().clamp_min(1e-30)).max().item()
+    assert rel < 1e-5, rel                     # fp32 products summed in fp32 (north_star: 1e-6 per entry)
+    ctx.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_numeric_rerun_with_new_values(ns, dtype):
+    """f1: one symbolic phase, the numeric phase twice with different values on the same pattern (AMG /
+    iterative solvers: HashSpGEMM_volta.hpp:1018-1031 SpGEMM_Hash_Numeric)."""
+    from nsparse_b200 import gen
+
+    a = gen.rmat_csr(13, 16, seed=5, dtype=dtype, values="small_int")
+    a.memcpy()
+    ctx = ns.Context(0)
+    d_rpt64, nnz, ip = ns.spgemm_symbolic(a, a, ctx)
+    col1, val1 = ns.spgemm_numeric(a, a, d_rpt64, nnz, ctx)
+    ctx.sync()
+    want1 = oracle.spgemm(a.rpt, a.col, a.val, a.rpt, a.col, a.val, acc_double=True)
+    assert np.array_equal(val1[:nnz].cpu().numpy(), want1[2])
+    a2 = ns.CSR(a.M, a.N, a.rpt, a.col, (a.val * 3 + 1).astype(dtype))
+    a2.memcpy()
+    col2, val2 = ns.spgemm_numeric(a2, a2, d_rpt64, nnz, ctx)
+    ctx.sync()
+    want2 = oracle.spgemm(a2.rpt, a2.col, a2.val, a2.rpt, a2.col, a2.val, acc_double=True)
+    assert np.array_equal(col2[:nnz].cpu().numpy(), want2[1]) and np.array_equal(col1[:nnz].cpu().numpy(), want2[1])
+    assert np.array_equal(val2[:nnz].cpu().numpy(), want2[2])
+    ctx.close()
