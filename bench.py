@@ -222,6 +222,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL prints its version banner on stdout otherwise
         dist.init_process_group("nccl", device_id=dev)
     dtype = np.float32
     tdt = torch.float32
@@ -249,9 +252,11 @@ def run_ours(args):
     # -------- one step ------------------------------------------------------------------------
     state = {}
 
+    peers = ns.PeerBuffers(ctx, fused=not args.unfused_push) if world > 1 and not args.nccl_gather else None
+
     def step():
         if world > 1:
-            c = ns.spgemm_kernel_hash_mgpu(a_loc, a, cuts, a.M, total_ip, ctx)
+            c = ns.spgemm_kernel_hash_mgpu(a_loc, a, cuts, a.M, total_ip, ctx, peers=peers)
         else:
             c = ns.spgemm_kernel_hash(a_loc, a, ctx)
         state["c"] = c
@@ -270,7 +275,9 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    c = None
     for _ in range(args.steps):
+        c = None                       # the previous product (78 GB at scale 20) goes before the next is made
         c = step()
         state.pop("c", None)
     e1.record()
@@ -355,8 +362,13 @@ def run_ours(args):
                                     "duplicates merged", "gen_seconds": gen_s,
                        "l2_policy": "each step writes nnz_C*8 bytes of C (>> 126 MB L2) and streams A/B "
                                     "(132 MB); no explicit flush",
-                       "parallelism": f"row-block x{world} by equal intermediate products, B replicated, "
-                                      "NCCL allgatherv of C" if world > 1 else "single GPU"},
+                       "parallelism": (f"row-block x{world} by equal intermediate products, B replicated, allgatherv of C: "
+                                       + ("NCCL broadcasts" if args.nccl_gather else
+                                          "a copy kernel stores the finished block into all peers over NVLink "
+                                          "(nsp_push_to_peers)" if args.unfused_push else
+                                          "fused: the numeric kernels store every chunk of C into all peers over NVLink "
+                                          "as they produce it (nsp_spgemm_set_peers)"))
+                       if world > 1 else "single GPU"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
         }
         if spmv is not None:
@@ -460,6 +472,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--spmv-grid", type=int, default=4096)
+    ap.add_argument("--unfused-push", action="store_true", help="N > 1: push the block after the numeric phase")
+    ap.add_argument("--nccl-gather", action="store_true", help="N > 1: gather C with NCCL broadcasts instead of peer stores")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-spmv", action="store_true")

@@ -114,6 +114,33 @@ int nsp_spgemm_host_drain(nsp_context *ctx, void *h_stage, size_t stage_bytes,
 int nsp_spgemm_host_release(nsp_context *ctx);
 
 /* ------------------------------------------------------------------------------------
+ * multi-GPU: allgatherv of C's row blocks over NVLink peer memory (new; the reference is single
+ * GPU).  Every rank owns one full-size buffer per array of C; the buffers of the other ranks are
+ * mapped into this process (CUDA IPC) and a rank PUSHES its block to all of them with plain
+ * stores, at the displacement the block has in the full matrix -- one kernel per array, no
+ * staging, no per-peer launch.  d_peer_bases: HOST array of `npeers` device pointers (the base of
+ * the same array on every destination, any of which may be local); the block is
+ * [byte_offset, byte_offset + nbytes) of every destination and starts at d_src; byte_offset, nbytes
+ * and the pointers must be multiples of 4 bytes.
+ * ---------------------------------------------------------------------------------- */
+/* cudaMalloc + cudaIpcGetMemHandle: a buffer other processes of this node can map.  handle: 64 bytes. */
+int nsp_peer_alloc(nsp_context *ctx, size_t bytes, void **d_ptr, unsigned char *handle64);
+/* cudaIpcOpenMemHandle on the context's device (peer access to the exporting GPU is enabled lazily) */
+int nsp_peer_open(nsp_context *ctx, const unsigned char *handle64, void **d_ptr);
+int nsp_peer_close(nsp_context *ctx, void *d_ptr);
+int nsp_peer_free(nsp_context *ctx, void *d_ptr);
+/* Fused numeric phase + allgatherv: after this call nsp_spgemm_numeric_* stores every entry of C it
+ * produces not only at d_c_col / d_c_val but also at d_peer_col[p] / d_peer_val[p] + elem_offset + (the
+ * same index) for p < npeers (at most 7): the bases of the FULL C.col / C.val arrays of the other GPUs and
+ * the displacement of this rank's row block in them.  The heavy rows are stored by the kernel that
+ * computes them, chunk by chunk, with the same coalesced stores as the local copy; a follow-up kernel
+ * pushes the remaining rows.  npeers == 0 switches it off. */
+int nsp_spgemm_set_peers(nsp_context *ctx, int npeers, void *const *d_peer_col, void *const *d_peer_val,
+                         long long elem_offset);
+int nsp_push_to_peers(nsp_context *ctx, int npeers, void *const *d_peer_bases, size_t byte_offset,
+                      const void *d_src, size_t nbytes);
+
+/* ------------------------------------------------------------------------------------
  * AMB SpMV, y = A * x
  * ---------------------------------------------------------------------------------- */
 

@@ -64,6 +64,12 @@ SIGNATURES = {
     "nsp_spmv_amb_host_s": (C.c_int, [vp, C.POINTER(nsp_amb), vp, vp]),
     "nsp_spmv_amb_host_d": (C.c_int, [vp, C.POINTER(nsp_amb), vp, vp]),
     "nsp_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "nsp_peer_alloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp), C.c_char_p]),
+    "nsp_peer_open": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
+    "nsp_peer_close": (C.c_int, [vp, vp]),
+    "nsp_peer_free": (C.c_int, [vp, vp]),
+    "nsp_spgemm_set_peers": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), ll]),
+    "nsp_push_to_peers": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.c_size_t, vp, C.c_size_t]),
     "nsp_gen_rmat_edges": (C.c_int, [C.c_int, ll, C.c_ulonglong, vp, vp]),
 }
 

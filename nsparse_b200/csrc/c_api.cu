@@ -70,6 +70,122 @@ int nsp_set_option(nsp_context *ctx, const char *name, long long value)
     return 0;
 }
 
+// ---- allgatherv over peer memory ------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+struct PeerList {
+    char *base[kMaxPeers];
+};
+
+// Source and destinations share the byte offset modulo 16 (all bases are 256-byte aligned allocations),
+// so one head / 16-byte body / tail split serves every copy.  Stores to a peer travel over NVLink as
+// posted writes; the loads are the only dependent step.
+__global__ void __launch_bounds__(256)
+push_to_peers_kernel(PeerList peers, int npeers, size_t byte_offset, const char *__restrict__ src, size_t nbytes)
+{
+    const size_t mis = (16 - (byte_offset & 15)) & 15;
+    const size_t head = mis < nbytes ? mis : nbytes;
+    const size_t body = (nbytes - head) & ~size_t(15);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src + head);
+    for (size_t i = tid; i < body / 16; i += nth) {
+        uint4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(s4 + i));
+        for (int p = 0; p < npeers; ++p)
+            reinterpret_cast<uint4 *>(peers.base[p] + byte_offset + head)[i] = v;
+    }
+    // head and tail in 4-byte units
+    const size_t tail0 = head + body;
+    const size_t nsmall = head / 4 + (nbytes - tail0) / 4;
+    for (size_t i = tid; i < nsmall; i += nth) {
+        const size_t off = i < head / 4 ? i * 4 : tail0 + (i - head / 4) * 4;
+        const unsigned v = *reinterpret_cast<const unsigned *>(src + off);
+        for (int p = 0; p < npeers; ++p) *reinterpret_cast<unsigned *>(peers.base[p] + byte_offset + off) = v;
+    }
+}
+
+int nsp_peer_alloc(nsp_context *ctx, size_t bytes, void **d_ptr, unsigned char *handle64)
+{
+    NSP_REQUIRE_CTX(ctx);
+    if (!d_ptr || !handle64) return ctx->fail(NSP_ERR_ARG, "nsp_peer_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    NSP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    NSP_CUDA_TRY(ctx, cudaMalloc(d_ptr, bytes ? bytes : 16));
+    cudaIpcMemHandle_t h;
+    NSP_CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, *d_ptr));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+int nsp_peer_open(nsp_context *ctx, const unsigned char *handle64, void **d_ptr)
+{
+    NSP_REQUIRE_CTX(ctx);
+    if (!d_ptr || !handle64) return ctx->fail(NSP_ERR_ARG, "nsp_peer_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    NSP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    NSP_CUDA_TRY(ctx, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int nsp_peer_close(nsp_context *ctx, void *d_ptr)
+{
+    NSP_REQUIRE_CTX(ctx);
+    if (d_ptr) NSP_CUDA_TRY(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
+
+int nsp_peer_free(nsp_context *ctx, void *d_ptr)
+{
+    NSP_REQUIRE_CTX(ctx);
+    if (d_ptr) NSP_CUDA_TRY(ctx, cudaFree(d_ptr));
+    return 0;
+}
+
+int nsp_spgemm_set_peers(nsp_context *ctx, int npeers, void *const *d_peer_col, void *const *d_peer_val,
+                         long long elem_offset)
+{
+    NSP_REQUIRE_CTX(ctx);
+    if (npeers < 0 || npeers > nsp::kMaxPeerOut || (npeers > 0 && (!d_peer_col || !d_peer_val)) || elem_offset < 0)
+        return ctx->fail(NSP_ERR_ARG, "nsp_spgemm_set_peers: bad argument (at most 7 peers)");
+    nsp::PeerOut po;
+    po.n = npeers;
+    po.off = elem_offset;
+    for (int p = 0; p < npeers; ++p) {
+        po.col[p] = static_cast<int *>(d_peer_col[p]);
+        po.val[p] = d_peer_val[p];
+    }
+    ctx->peer_out = po;
+    return 0;
+}
+
+int nsp_push_to_peers(nsp_context *ctx, int npeers, void *const *d_peer_bases, size_t byte_offset,
+                      const void *d_src, size_t nbytes)
+{
+    NSP_REQUIRE_CTX(ctx);
+    if (npeers < 0 || npeers > kMaxPeers || (npeers > 0 && !d_peer_bases) || (nbytes > 0 && !d_src))
+        return ctx->fail(NSP_ERR_ARG, "nsp_push_to_peers: bad argument");
+    if (((byte_offset | nbytes | reinterpret_cast<uintptr_t>(d_src)) & 3) != 0)
+        return ctx->fail(NSP_ERR_ARG, "nsp_push_to_peers: offsets and sizes must be multiples of 4 bytes");
+    if (npeers == 0 || nbytes == 0) return 0;
+    PeerList pl;
+    for (int p = 0; p < npeers; ++p) {
+        if ((reinterpret_cast<uintptr_t>(d_peer_bases[p]) & 15) != 0)
+            return ctx->fail(NSP_ERR_ARG, "nsp_push_to_peers: destination bases must be 16-byte aligned");
+        pl.base[p] = static_cast<char *>(d_peer_bases[p]);
+    }
+    if (((reinterpret_cast<uintptr_t>(d_src) - byte_offset) & 15) != 0)
+        return ctx->fail(NSP_ERR_ARG, "nsp_push_to_peers: source and destinations must share the offset modulo 16");
+    size_t want = (nbytes / 16 + 255) / 256;
+    int grid = (int)(want < (size_t)ctx->sm_count * 8 ? (want ? want : 1) : (size_t)ctx->sm_count * 8);
+    push_to_peers_kernel<<<grid, 256, 0, ctx->stream>>>(pl, npeers, byte_offset, static_cast<const char *>(d_src), nbytes);
+    ctx->launches += 1;
+    NSP_CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
 long long nsp_launch_count(nsp_context *ctx) { return ctx ? ctx->launches : 0; }
 
 int nsp_profile_dump(nsp_context *ctx, char *buf, size_t buflen)

@@ -25,6 +25,17 @@ constexpr int kEmptyKey = -1;              // columns are >= 0, so -1 marks a fr
 // the SpGEMM does not depend on the hash.
 constexpr unsigned kHashMul = 0x9E3779B1u;
 
+// Peer copies of C for the fused compute + allgatherv of the multi-GPU SpGEMM: base pointers of the FULL
+// C.col / C.val arrays on the other GPUs (mapped with CUDA IPC) and the element displacement of this
+// rank's row block.  n == 0: single GPU.
+constexpr int kMaxPeerOut = 7;
+struct PeerOut {
+    int n = 0;
+    long long off = 0;
+    int *col[kMaxPeerOut] = {};
+    void *val[kMaxPeerOut] = {};
+};
+
 struct Error {
     int code;
     std::string msg;

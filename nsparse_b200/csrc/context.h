@@ -82,6 +82,7 @@ struct nsp_context {
     long long opt_lanes_per_brow = 0;    // 0: pick from nnz(B)/K
 
     nsp_spgemm_state sp;
+    nsp::PeerOut peer_out;   // nsp_spgemm_set_peers
     nsp_host_result host;
 
     long long launches = 0;

@@ -177,7 +177,8 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                   const int *__restrict__ b_col, const real *__restrict__ b_val,
                   const long long *__restrict__ c_rpt, int *__restrict__ c_col, real *__restrict__ c_val,
                   const int *__restrict__ row_perm, int *__restrict__ bins, int bin_lo, int bin_hi,
-                  int queue, int N, int wshift, int cap, int b_vec_end, int dbg, long long *phase_cycles)
+                  int queue, int N, int wshift, int cap, int b_vec_end, int dbg, long long *phase_cycles,
+                  const __grid_constant__ PeerOut peer)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = BS / 32;
@@ -367,10 +368,28 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                 PH(8);
                 real *cv = c_val + out + r0;
                 int *cc = c_col + out + r0;
-                for (int i = t; i < cnt; i += BS) {
-                    const int j = acc_swz(i);
-                    cv[i] = acc[j];
-                    cc[i] = cols[j];
+                if (peer.n == 0) {
+                    for (int i = t; i < cnt; i += BS) {
+                        const int j = acc_swz(i);
+                        cv[i] = acc[j];
+                        cc[i] = cols[j];
+                    }
+                } else {
+                    // fused allgatherv: the finished chunk goes to this GPU's C and, with the same coalesced
+                    // stores, to the C of every peer over NVLink (posted writes: nothing waits for them)
+                    const long long g = peer.off + out + r0;
+                    for (int i = t; i < cnt; i += BS) {
+                        const int j = acc_swz(i);
+                        const real v = acc[j];
+                        const int c = cols[j];
+                        cv[i] = v;
+                        cc[i] = c;
+#pragma unroll 1
+                        for (int p = 0; p < peer.n; ++p) {
+                            static_cast<real *>(peer.val[p])[g + i] = v;
+                            peer.col[p][g + i] = c;
+                        }
+                    }
                 }
                 __syncthreads();                       // the next chunk reuses the buffers
                 PH(9);
@@ -405,7 +424,13 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                     }
                     __syncthreads();
                     int *cc = c_col + out + r0;
-                    for (int i = t; i < cnt; i += BS) cc[i] = cols[i];
+                    const long long g = peer.off + out + r0;
+                    for (int i = t; i < cnt; i += BS) {
+                        const int c = cols[i];
+                        cc[i] = c;
+#pragma unroll 1
+                        for (int p = 0; p < peer.n; ++p) peer.col[p][g + i] = c;
+                    }
                     __syncthreads();
                 }
                 PH(6);
@@ -429,6 +454,18 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                     run_parts<BS, true, real>(t, total, b_col, b_val, s_part, add_red);
                     PH(10);
                 }
+                if (peer.n > 0) {
+                    // the row is complete once every thread's reds are performed: read it back from L2 and
+                    // hand it to the peers (fused allgatherv of the red.global rows)
+                    __threadfence();
+                    __syncthreads();
+                    const long long g = peer.off + out;
+                    for (int i = t; i < tile_nnz; i += BS) {
+                        const real v = __ldcg(cv + i);
+#pragma unroll 1
+                        for (int p = 0; p < peer.n; ++p) static_cast<real *>(peer.val[p])[g + i] = v;
+                    }
+                }
             }
             out += tile_nnz;
         }
@@ -440,6 +477,39 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
     }
 #endif
 #undef PH
+}
+
+// Rows of C that num_bitmap_kernel did not store into the peers itself (see PeerOut): everything below
+// the bitmap class.  A CTA takes eight consecutive rows: short rows one warp each, long rows all eight.
+template <typename real>
+__global__ void __launch_bounds__(256)
+push_rows_kernel(int M, const int *__restrict__ a_rpt, const long long *__restrict__ c_rpt,
+                 const int *__restrict__ c_col, const real *__restrict__ c_val, int bm_bin, int shift, bool fused_class,
+                 const __grid_constant__ PeerOut peer)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = blockIdx.x * 8; base < M; base += gridDim.x * 8) {
+        for (int r = 0; r < 8 && base + r < M; ++r) {
+            const int i = base + r;
+            const long long s = c_rpt[i], e = c_rpt[i + 1];
+            const long long n = e - s;
+            if (n == 0) continue;
+            const bool fused = fused_class && log_bin((int)(n < 0x7fffffffll ? n : 0x7fffffffll), shift) >= bm_bin;
+            if (fused) continue;
+            const bool whole_cta = n > 1024;
+            if (!whole_cta && wid != r) continue;
+            const long long first = s + (whole_cta ? threadIdx.x : lane);
+            const int stride = whole_cta ? 256 : 32;
+            for (long long k = first; k < e; k += stride) {
+                const int c = c_col[k];
+                const real v = c_val[k];
+                for (int p = 0; p < peer.n; ++p) {
+                    peer.col[p][peer.off + k] = c;
+                    static_cast<real *>(peer.val[p])[peer.off + k] = v;
+                }
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -546,7 +616,7 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
         num_prof_class(ctx, "num_bitmap", bm_bin, kNumBins - 1);
         kern<<<grid, 1024, smem, ctx->stream>>>(NSP_NUM_ARGS, bm_bin, kNumBins - 1, 4, N, wshift, cap,
                                                 b_vec_end_of(ctx, b_col), (int)ctx->opt_debug,
-                                                ctx->opt_phase_timing ? ctx->phase_cycles() : nullptr);
+                                                ctx->opt_phase_timing ? ctx->phase_cycles() : nullptr, ctx->peer_out);
         ctx->prof_end();
         ctx->launches += 1;
         NSP_CUDA_TRY(ctx, cudaGetLastError());
@@ -582,6 +652,14 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
         num_pwarp_kernel<real><<<grid, 256, 0, ctx->stream>>>(a_rpt, a_col, a_val, b_rpt, b_col, b_val,
                                                               c_rpt64, c_col, c_val, sp.d_row_perm, sp.d_bins);
         ctx->prof_end();
+        ctx->launches += 1;
+        NSP_CUDA_TRY(ctx, cudaGetLastError());
+    }
+    if (ctx->peer_out.n > 0) {
+        // rows the heavy kernel did not push itself: the light classes and the multi-slab rows
+        const int grid = num_imin(((long long)M + 7) / 8, (long long)sms * 16);
+        push_rows_kernel<real><<<grid, 256, 0, ctx->stream>>>(M, a_rpt, c_rpt64, c_col, c_val, bm_bin, kNumShift,
+                                                            num_rows_in(sp, bm_bin, kNumBins - 1) > 0, ctx->peer_out);
         ctx->launches += 1;
         NSP_CUDA_TRY(ctx, cudaGetLastError());
     }

@@ -44,31 +44,23 @@ def row_block(a: CSR, r0: int, r1: int) -> CSR:
                f"{a.matrix_name}[{r0}:{r1}]")
 
 
-def allgatherv_csr(rpt_local, col_local, val_local, nnz_local: int, cuts, n_rows: int, group=None):
-    """Gather the row blocks of C held by the ranks of `group` into the full matrix on every rank.
-
-    rpt_local: int64 tensor [rows_local + 1] starting at 0; col_local / val_local: at least nnz_local
-    entries.  Returns (rpt int64 [n_rows + 1], col, val, nnz_total).  Works on any backend / device."""
+def _gather_sizes(nnz_local: int, dev, group=None):
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    dev = rpt_local.device
     sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(sizes, torch.tensor([nnz_local], dtype=torch.int64, device=dev), group=group)
     sz = [int(s.item()) for s in sizes]
-    disp = np.concatenate([[0], np.cumsum(sz)]).astype(np.int64)
-    tot = int(disp[-1])
-    col = torch.empty(max(tot, 1), dtype=col_local.dtype, device=dev)
-    val = torch.empty(max(tot, 1), dtype=val_local.dtype, device=dev)
-    rpt = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
-    # every rank puts its block at its displacement of the final buffers, then block r is broadcast
-    # from rank r in place (NCCL: one ncclBroadcast per block and array; nothing is staged or padded)
-    lo, hi = int(disp[rank]), int(disp[rank + 1])
-    col[lo:hi].copy_(col_local[:nnz_local])
-    val[lo:hi].copy_(val_local[:nnz_local])
-    rpt[cuts[rank]:cuts[rank + 1]].copy_(rpt_local[:-1] + lo)
+    return np.concatenate([[0], np.cumsum(sz)]).astype(np.int64)
+
+
+def _broadcast_blocks(rpt, col, val, disp, cuts, group=None):
+    """Block r of every array is broadcast from rank r in place (NCCL: one ncclBroadcast per block and
+    array; nothing is staged or padded)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
     works = []
     for r in range(world):
         src = dist.get_global_rank(group, r) if group is not None else r
@@ -77,15 +69,188 @@ def allgatherv_csr(rpt_local, col_local, val_local, nnz_local: int, cuts, n_rows
                 works.append(dist.broadcast(buf[int(a):int(b)], src=src, group=group, async_op=True))
     for w in works:
         w.wait()
+
+
+def allgatherv_csr(rpt_local, col_local, val_local, nnz_local: int, cuts, n_rows: int, group=None):
+    """Gather the row blocks of C held by the ranks of `group` into the full matrix on every rank.
+
+    rpt_local: int64 tensor [rows_local + 1] starting at 0; col_local / val_local: at least nnz_local
+    entries.  Returns (rpt int64 [n_rows + 1], col, val, nnz_total).  Works on any backend / device."""
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    dev = rpt_local.device
+    disp = _gather_sizes(nnz_local, dev, group)
+    tot = int(disp[-1])
+    col = torch.empty(max(tot, 1), dtype=col_local.dtype, device=dev)
+    val = torch.empty(max(tot, 1), dtype=val_local.dtype, device=dev)
+    rpt = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+    lo, hi = int(disp[rank]), int(disp[rank + 1])
+    col[lo:hi].copy_(col_local[:nnz_local])
+    val[lo:hi].copy_(val_local[:nnz_local])
+    rpt[cuts[rank]:cuts[rank + 1]].copy_(rpt_local[:-1] + lo)
+    _broadcast_blocks(rpt, col, val, disp, cuts, group)
     rpt[n_rows] = tot
     return rpt, col, val, tot
 
 
-def spgemm_kernel_hash_mgpu(a_local: CSR, b: CSR, cuts, n_rows: int, total_ip: int, ctx=None, group=None) -> DeviceCSR64:
-    """This rank's block through the single-GPU pipeline, then the gather.  a_local and b must have
-    been memcpy()'d to this rank's GPU."""
-    from .spgemm import spgemm_kernel_hash
+class _DeviceArray:
+    """Raw device memory as something torch.as_tensor understands (the memory stays owned by PeerBuffers)."""
 
-    c = spgemm_kernel_hash(a_local, b, ctx)
-    rpt, col, val, tot = allgatherv_csr(c.d_rpt64, c.d_col, c.d_val, c.nnz, cuts, n_rows, group)
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+class PeerBuffers:
+    """The full-size C arrays of every rank, mapped into this process with CUDA IPC (nsp_peer_alloc /
+    nsp_peer_open), so that a rank can store its row block straight into every other GPU's copy over
+    NVLink / NVSwitch.  Grow-only: handles are exchanged again only when a product needs more room."""
+
+    _TYPES = {"col": ("<i4", 4), "rpt": ("<i8", 8)}
+
+    def __init__(self, ctx, group=None, fused=True):
+        """fused: the numeric kernels store into the peers themselves (nsp_spgemm_set_peers); otherwise the
+        block is pushed by a copy kernel after the numeric phase (nsp_push_to_peers)."""
+        self.ctx, self.group, self.fused = ctx, group, fused
+        self.cap_nnz, self.n_rows, self.dtype = -1, -1, None
+        self.col = self.val = self.rpt = None
+        self._own, self._opened = {}, []
+
+    def _others(self, key):
+        import torch.distributed as dist
+
+        rank = dist.get_rank(self.group)
+        return [p for r, p in enumerate(self.ptrs[key]) if r != rank]
+
+    def set_fused_targets(self, elem_offset: int):
+        import ctypes as C
+
+        cols, vals = self._others("col"), self._others("val")
+        if len(cols) > 7:
+            raise ValueError("fused peer stores support at most 8 GPUs")
+        self.ctx.check(self.ctx.lib.nsp_spgemm_set_peers(self.ctx.handle, len(cols), (C.c_void_p * len(cols))(*cols),
+                                                         (C.c_void_p * len(vals))(*vals), elem_offset))
+
+    def clear_fused_targets(self):
+        self.ctx.check(self.ctx.lib.nsp_spgemm_set_peers(self.ctx.handle, 0, None, None, 0))
+
+    def release(self):
+        import ctypes as C
+
+        self.col = self.val = self.rpt = None
+        for p in self._opened:
+            self.ctx.lib.nsp_peer_close(self.ctx.handle, C.c_void_p(p))
+        for p in self._own.values():
+            self.ctx.lib.nsp_peer_free(self.ctx.handle, C.c_void_p(p))
+        self._own, self._opened = {}, []
+        self.cap_nnz = -1
+
+    def ensure(self, tot: int, n_rows: int, tdt, dev):
+        """Collective (every rank calls it with the same arguments)."""
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        if tot <= self.cap_nnz and n_rows == self.n_rows and tdt == self.dtype:
+            return
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        torch.cuda.synchronize(dev)
+        dist.barrier(self.group)               # nobody still pushes into the buffers that are about to go
+        self.release()
+        torch.cuda.empty_cache()
+        cap = max(int(tot), 4)
+        vt = ("<f8", 8) if tdt == torch.float64 else ("<f4", 4)
+        spec = {"col": (cap,) + self._TYPES["col"], "val": (cap,) + vt, "rpt": (n_rows + 1,) + self._TYPES["rpt"]}
+        handles = {}
+        for k, (n, typestr, es) in spec.items():
+            p, h = C.c_void_p(), C.create_string_buffer(64)
+            self.ctx.check(self.ctx.lib.nsp_peer_alloc(self.ctx.handle, n * es, C.byref(p), h))
+            self._own[k] = p.value
+            handles[k] = h.raw
+            setattr(self, k, torch.as_tensor(_DeviceArray(p.value, n, typestr), device=dev))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, handles, group=self.group)
+        self.ptrs = {"col": [], "val": [], "rpt": []}
+        for r in range(world):
+            for k in ("col", "val", "rpt"):
+                if r == rank:
+                    self.ptrs[k].append(self._own[k])
+                else:
+                    p = C.c_void_p()
+                    self.ctx.check(self.ctx.lib.nsp_peer_open(self.ctx.handle, everyone[r][k], C.byref(p)))
+                    self._opened.append(p.value)
+                    self.ptrs[k].append(p.value)
+        self.cap_nnz, self.n_rows, self.dtype = cap, n_rows, tdt
+        dist.barrier(self.group)
+
+    def push(self, key: str, src, elem_offset: int):
+        """Store `src` (a slice of this rank's own array `key`, starting at element elem_offset) into the
+        same place of every OTHER rank's array."""
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        rank = dist.get_rank(self.group)
+        dst = [p for r, p in enumerate(self.ptrs[key]) if r != rank]
+        if not dst or src.numel() == 0:
+            return
+        arr = (C.c_void_p * len(dst))(*dst)
+        es = src.element_size()
+        self.ctx.check(self.ctx.lib.nsp_push_to_peers(self.ctx.handle, len(dst), arr, elem_offset * es,
+                                                      C.c_void_p(src.data_ptr()), src.numel() * es))
+
+
+def spgemm_kernel_hash_mgpu(a_local: CSR, b: CSR, cuts, n_rows: int, total_ip: int, ctx=None, group=None,
+                            peers: "PeerBuffers | None" = None) -> DeviceCSR64:
+    """This rank's block through the single-GPU pipeline, then the gather.  a_local and b must have
+    been memcpy()'d to this rank's GPU.  The numeric phase writes the block straight into its place in
+    the full C (the displacements are known after the symbolic phase), so a rank never holds more than
+    one copy of C: 78 GB at R-MAT scale 20."""
+    import torch
+    import torch.distributed as dist
+
+    from .spgemm import spgemm_numeric, spgemm_symbolic
+
+    rank = dist.get_rank(group)
+    d_rpt64, nnz, _ = spgemm_symbolic(a_local, b, ctx)
+    dev = d_rpt64.device
+    disp = _gather_sizes(nnz, dev, group)
+    tot = int(disp[-1])
+    tdt = torch.float64 if a_local.dtype == np.float64 else torch.float32
+    if peers is not None:
+        # NVLink push: the block is computed in place and stored into every peer's arrays by one kernel
+        # per array (nsp_push_to_peers); the exchange of the sizes above is also the point after which no
+        # rank still reads the previous product.
+        peers.ensure(tot, n_rows, tdt, dev)
+        lo, hi = int(disp[rank]), int(disp[rank + 1])
+        col, val, rpt = peers.col, peers.val, peers.rpt
+        out = (col[lo:max(hi, lo + 1)], val[lo:max(hi, lo + 1)])
+        if peers.fused:
+            # the numeric kernels store every entry into all the peers as they produce it
+            peers.set_fused_targets(lo)
+            try:
+                spgemm_numeric(a_local, b, d_rpt64, nnz, ctx, out=out)
+            finally:
+                peers.clear_fused_targets()
+        else:
+            spgemm_numeric(a_local, b, d_rpt64, nnz, ctx, out=out)
+            peers.push("col", col[lo:hi], lo)
+            peers.push("val", val[lo:hi], lo)
+        rpt[cuts[rank]:cuts[rank + 1]].copy_(d_rpt64[:-1] + lo)
+        rpt[n_rows] = tot
+        peers.push("rpt", rpt[cuts[rank]:cuts[rank + 1]], cuts[rank])
+        torch.cuda.current_stream(dev).synchronize()
+        dist.barrier(group)                      # every block of every rank has landed
+        return DeviceCSR64(n_rows, b.N, rpt, col[:max(tot, 1)], val[:max(tot, 1)], tot, total_ip)
+    col = torch.empty(max(tot, 1), dtype=torch.int32, device=dev)
+    val = torch.empty(max(tot, 1), dtype=tdt, device=dev)
+    rpt = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+    lo, hi = int(disp[rank]), int(disp[rank + 1])
+    spgemm_numeric(a_local, b, d_rpt64, nnz, ctx, out=(col[lo:max(hi, lo + 1)], val[lo:max(hi, lo + 1)]))
+    rpt[cuts[rank]:cuts[rank + 1]].copy_(d_rpt64[:-1] + lo)
+    _broadcast_blocks(rpt, col, val, disp, cuts, group)
+    rpt[n_rows] = tot
     return DeviceCSR64(n_rows, b.N, rpt, col, val, tot, total_ip)
