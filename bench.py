@@ -252,7 +252,9 @@ def run_ours(args):
     # -------- one step ------------------------------------------------------------------------
     state = {}
 
-    peers = ns.PeerBuffers(ctx, fused=not args.unfused_push) if world > 1 and not args.nccl_gather else None
+    peers = None
+    if world > 1 and not args.nccl_gather:
+        peers = ns.PeerBuffers(ctx, fused=args.gather == "fused", pieces=0 if args.gather == "push" else args.pieces)
 
     def step():
         if world > 1:
@@ -262,9 +264,20 @@ def run_ours(args):
         state["c"] = c
         return c
 
-    for _ in range(args.warmup):
-        step()
+    for w in range(args.warmup):
+        c = step()
         state.pop("c", None)
+        if w == 0 and world > 1 and not args.ip_partition:
+            # Re-cut the row blocks with the counts of the first product: a rank's time is its compute
+            # (~ intermediate products) plus what it sends (~ its entries of C times the peers), see
+            # partition_rows_by_cost.  8 bytes per entry and peer at ~700 GB/s against ~10 ps per product.
+            c_rpt = c.d_rpt64.cpu().numpy()
+            del c
+            weight = args.nnz_weight if args.nnz_weight >= 0 else 1.15 * (world - 1)
+            cuts, _ = ns.partition_rows_by_cost(a.rpt, a.col, a.rpt, c_rpt, world, weight)
+            a_loc = ns.row_block(a, cuts[rank], cuts[rank + 1])
+            a_loc.memcpy(local)
+        c = None
     barrier()
     ctx.profile(True)
     ctx.profile_dump()
@@ -295,12 +308,24 @@ def run_ours(args):
         ln = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(ln)
         launches = int(ln.item())
+        mine = torch.tensor([sum(p[1] for p in prof) / args.steps, float(cuts[rank + 1] - cuts[rank])],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"kernel_ms": [round(float(x[0]), 2) for x in allr], "rows": [int(x[1]) for x in allr]}
+    else:
+        per_rank = None
     ms_step = ms / args.steps
     gflops = 2.0 * ip / ms_step / 1e6
 
     # -------- roofline of the dominant kernel (rank 0's launches) ----------------------------------
     agg = {}
     for name, kms, rows, kip, alen, nout in prof:
+        if name.endswith("_long"):
+            # second launch over the SAME row class (its rows with more than 1024 entries of A): its time
+            # belongs to the class, whose rows / products / bytes the first launch already reported
+            agg.setdefault(name[:-5], {"ms": 0.0, "n": 0, "bytes": 0})["ms"] += kms
+            continue
         d = agg.setdefault(name, {"ms": 0.0, "n": 0, "bytes": 0})
         d["ms"] += kms
         d["n"] += 1
@@ -365,12 +390,18 @@ def run_ours(args):
                        "parallelism": (f"row-block x{world} by equal intermediate products, B replicated, allgatherv of C: "
                                        + ("NCCL broadcasts" if args.nccl_gather else
                                           "a copy kernel stores the finished block into all peers over NVLink "
-                                          "(nsp_push_to_peers)" if args.unfused_push else
+                                          "(nsp_push_to_peers)" if args.gather == "push" else
                                           "fused: the numeric kernels store every chunk of C into all peers over NVLink "
-                                          "as they produce it (nsp_spgemm_set_peers)"))
+                                          "as they produce it (nsp_spgemm_set_peers)" if args.gather == "fused" else
+                                          f"pipelined: the block is computed in {args.pieces} pieces, the copy engines carry "
+                                          "every finished piece to all peers over NVLink while the next is computed"))
                        if world > 1 else "single GPU"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
         }
+        if per_rank is not None:
+            line["config"]["per_rank"] = per_rank
+            line["config"]["partition"] = ("equal intermediate products" if args.ip_partition else
+                                           "intermediate products + w * nnz(C_i), counts from the first warm-up product")
         if spmv is not None:
             line["spmv"] = spmv
         print(json.dumps(line), flush=True)
@@ -472,7 +503,11 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--spmv-grid", type=int, default=4096)
-    ap.add_argument("--unfused-push", action="store_true", help="N > 1: push the block after the numeric phase")
+    ap.add_argument("--gather", default="fused", choices=["pipelined", "fused", "push"],
+                    help="N > 1: how a rank's block of C reaches the peers (see nsparse_b200/multi_gpu.py)")
+    ap.add_argument("--pieces", type=int, default=4)
+    ap.add_argument("--ip-partition", action="store_true", help="N > 1: keep the equal-intermediate-products row blocks")
+    ap.add_argument("--nnz-weight", type=float, default=-1.0, help="N > 1: weight of nnz(C_i) in the row cost (default 1.15 (N-1))")
     ap.add_argument("--nccl-gather", action="store_true", help="N > 1: gather C with NCCL broadcasts instead of peer stores")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -89,6 +89,18 @@ int nsp_spgemm_numeric_d(nsp_context *ctx, int M, int K, int N,
                          const int *d_b_rpt, const int *d_b_col, const double *d_b_val,
                          const long long *d_c_rpt64, int *d_c_col, double *d_c_val);
 
+/* The numeric phase for the rows [row0, row0 + nrows) only; every pointer is that of the FULL array.  The
+ * multi-GPU pipeline calls it piece by piece so that finished pieces of C travel to the other GPUs (copy
+ * engines over NVLink) while the next piece is computed. */
+int nsp_spgemm_numeric_rows_s(nsp_context *ctx, int M, int K, int N, int row0, int nrows,
+                              const int *d_a_rpt, const int *d_a_col, const float *d_a_val,
+                              const int *d_b_rpt, const int *d_b_col, const float *d_b_val,
+                              const long long *d_c_rpt64, int *d_c_col, float *d_c_val);
+int nsp_spgemm_numeric_rows_d(nsp_context *ctx, int M, int K, int N, int row0, int nrows,
+                              const int *d_a_rpt, const int *d_a_col, const double *d_a_val,
+                              const int *d_b_rpt, const int *d_b_col, const double *d_b_val,
+                              const long long *d_c_rpt64, int *d_c_col, double *d_c_val);
+
 /* Narrow an int64 row pointer to the int32 one sfCSR carries; NSP_ERR_OVERFLOW if
  * nnz > INT_MAX (the reference silently wraps, kernel_spgemm_hash_d.cu:1183). */
 int nsp_rpt64_to_rpt32(nsp_context *ctx, int M, const long long *d_rpt64, long long nnz, int *d_rpt32);
@@ -129,6 +141,10 @@ int nsp_peer_alloc(nsp_context *ctx, size_t bytes, void **d_ptr, unsigned char *
 int nsp_peer_open(nsp_context *ctx, const unsigned char *handle64, void **d_ptr);
 int nsp_peer_close(nsp_context *ctx, void *d_ptr);
 int nsp_peer_free(nsp_context *ctx, void *d_ptr);
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) on `cuda_stream` (NULL: the context's stream): with
+ * a destination opened by nsp_peer_open this is a copy-engine transfer over NVLink that needs no SM. */
+int nsp_copy_async(nsp_context *ctx, void *d_dst, const void *d_src, size_t bytes, void *cuda_stream);
+
 /* Fused numeric phase + allgatherv: after this call nsp_spgemm_numeric_* stores every entry of C it
  * produces not only at d_c_col / d_c_val but also at d_peer_col[p] / d_peer_val[p] + elem_offset + (the
  * same index) for p < npeers (at most 7): the bases of the FULL C.col / C.val arrays of the other GPUs and
@@ -139,6 +155,12 @@ int nsp_spgemm_set_peers(nsp_context *ctx, int npeers, void *const *d_peer_col, 
                          long long elem_offset);
 int nsp_push_to_peers(nsp_context *ctx, int npeers, void *const *d_peer_bases, size_t byte_offset,
                       const void *d_src, size_t nbytes);
+
+/* nsp_push_to_peers through an NVSwitch multicast address (NVLS): d_multicast_base is the multicast
+ * mapping of the same array on all GPUs; one multimem.st per 16 bytes reaches every copy, the local one
+ * included.  Same alignment rules. */
+int nsp_push_multicast(nsp_context *ctx, void *d_multicast_base, size_t byte_offset, const void *d_src,
+                       size_t nbytes);
 
 /* ------------------------------------------------------------------------------------
  * AMB SpMV, y = A * x

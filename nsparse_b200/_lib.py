@@ -47,6 +47,8 @@ SIGNATURES = {
                                       C.POINTER(ll), C.POINTER(ll)]),
     "nsp_spgemm_numeric_s": (C.c_int, [vp, C.c_int, C.c_int, C.c_int] + [vp] * 9),
     "nsp_spgemm_numeric_d": (C.c_int, [vp, C.c_int, C.c_int, C.c_int] + [vp] * 9),
+    "nsp_spgemm_numeric_rows_s": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [vp] * 9),
+    "nsp_spgemm_numeric_rows_d": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [vp] * 9),
     "nsp_rpt64_to_rpt32": (C.c_int, [vp, C.c_int, vp, ll, vp]),
     "nsp_spgemm_host_s": (C.c_int, [vp, C.c_int, C.c_int, C.c_int] + [vp] * 6 + [C.POINTER(ll)]),
     "nsp_spgemm_host_d": (C.c_int, [vp, C.c_int, C.c_int, C.c_int] + [vp] * 6 + [C.POINTER(ll)]),
@@ -68,7 +70,9 @@ SIGNATURES = {
     "nsp_peer_open": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
     "nsp_peer_close": (C.c_int, [vp, vp]),
     "nsp_peer_free": (C.c_int, [vp, vp]),
+    "nsp_copy_async": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
     "nsp_spgemm_set_peers": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), ll]),
+    "nsp_push_multicast": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t]),
     "nsp_push_to_peers": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.c_size_t, vp, C.c_size_t]),
     "nsp_gen_rmat_edges": (C.c_int, [C.c_int, ll, C.c_ulonglong, vp, vp]),
 }

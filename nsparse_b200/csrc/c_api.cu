@@ -144,6 +144,16 @@ int nsp_peer_free(nsp_context *ctx, void *d_ptr)
     return 0;
 }
 
+int nsp_copy_async(nsp_context *ctx, void *d_dst, const void *d_src, size_t bytes, void *cuda_stream)
+{
+    NSP_REQUIRE_CTX(ctx);
+    if (bytes == 0) return 0;
+    if (!d_dst || !d_src) return ctx->fail(NSP_ERR_ARG, "nsp_copy_async: bad argument");
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    NSP_CUDA_TRY(ctx, cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, st));
+    return 0;
+}
+
 int nsp_spgemm_set_peers(nsp_context *ctx, int npeers, void *const *d_peer_col, void *const *d_peer_val,
                          long long elem_offset)
 {
@@ -158,6 +168,55 @@ int nsp_spgemm_set_peers(nsp_context *ctx, int npeers, void *const *d_peer_col, 
         po.val[p] = d_peer_val[p];
     }
     ctx->peer_out = po;
+    return 0;
+}
+
+// The same through an NVSwitch multicast address: ONE multimem.st per 16 bytes, the switch replicates the
+// write into the buffer of every GPU bound to the multicast object (NVLS).
+__global__ void __launch_bounds__(256)
+push_multicast_kernel(char *mc_base, size_t byte_offset, const char *__restrict__ src, size_t nbytes)
+{
+    const size_t mis = (16 - (byte_offset & 15)) & 15;
+    const size_t head = mis < nbytes ? mis : nbytes;
+    const size_t body = (nbytes - head) & ~size_t(15);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src + head);
+    char *d = mc_base + byte_offset + head;
+    for (size_t i = tid; i < body / 16; i += nth) {
+        uint4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(s4 + i));
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(d + i * 16),
+                     "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)),
+                     "f"(__uint_as_float(v.w))
+                     : "memory");
+    }
+    const size_t tail0 = head + body;
+    const size_t nsmall = head / 4 + (nbytes - tail0) / 4;
+    for (size_t i = tid; i < nsmall; i += nth) {
+        const size_t off = i < head / 4 ? i * 4 : tail0 + (i - head / 4) * 4;
+        const unsigned v = *reinterpret_cast<const unsigned *>(src + off);
+        asm volatile("multimem.st.relaxed.sys.global.b32 [%0], %1;" ::"l"(mc_base + byte_offset + off), "r"(v) : "memory");
+    }
+}
+
+int nsp_push_multicast(nsp_context *ctx, void *d_multicast_base, size_t byte_offset, const void *d_src, size_t nbytes)
+{
+    NSP_REQUIRE_CTX(ctx);
+    if (!d_multicast_base || (nbytes > 0 && !d_src)) return ctx->fail(NSP_ERR_ARG, "nsp_push_multicast: bad argument");
+    if (((byte_offset | nbytes | reinterpret_cast<uintptr_t>(d_src)) & 3) != 0 ||
+        (reinterpret_cast<uintptr_t>(d_multicast_base) & 15) != 0 ||
+        ((reinterpret_cast<uintptr_t>(d_src) - byte_offset) & 15) != 0)
+        return ctx->fail(NSP_ERR_ARG, "nsp_push_multicast: alignment (see nsp_push_to_peers)");
+    if (nbytes == 0) return 0;
+    size_t want = (nbytes / 16 + 255) / 256;
+    int grid = (int)(want < (size_t)ctx->sm_count * 8 ? (want ? want : 1) : (size_t)ctx->sm_count * 8);
+    push_multicast_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<char *>(d_multicast_base), byte_offset,
+                                                         static_cast<const char *>(d_src), nbytes);
+    ctx->launches += 1;
+    NSP_CUDA_TRY(ctx, cudaGetLastError());
     return 0;
 }
 
@@ -244,6 +303,24 @@ int nsp_spgemm_numeric_d(nsp_context *ctx, int M, int K, int N, const int *d_a_r
     NSP_REQUIRE_CTX(ctx);
     return nsp::spgemm_numeric<double>(ctx, M, K, N, d_a_rpt, d_a_col, d_a_val, d_b_rpt, d_b_col, d_b_val,
                                        d_c_rpt64, d_c_col, d_c_val);
+}
+
+int nsp_spgemm_numeric_rows_s(nsp_context *ctx, int M, int K, int N, int row0, int nrows, const int *d_a_rpt,
+                              const int *d_a_col, const float *d_a_val, const int *d_b_rpt, const int *d_b_col,
+                              const float *d_b_val, const long long *d_c_rpt64, int *d_c_col, float *d_c_val)
+{
+    NSP_REQUIRE_CTX(ctx);
+    return nsp::spgemm_numeric<float>(ctx, M, K, N, d_a_rpt, d_a_col, d_a_val, d_b_rpt, d_b_col, d_b_val,
+                                      d_c_rpt64, d_c_col, d_c_val, row0, nrows);
+}
+
+int nsp_spgemm_numeric_rows_d(nsp_context *ctx, int M, int K, int N, int row0, int nrows, const int *d_a_rpt,
+                              const int *d_a_col, const double *d_a_val, const int *d_b_rpt, const int *d_b_col,
+                              const double *d_b_val, const long long *d_c_rpt64, int *d_c_col, double *d_c_val)
+{
+    NSP_REQUIRE_CTX(ctx);
+    return nsp::spgemm_numeric<double>(ctx, M, K, N, d_a_rpt, d_a_col, d_a_val, d_b_rpt, d_b_col, d_b_val,
+                                       d_c_rpt64, d_c_col, d_c_val, row0, nrows);
 }
 
 int nsp_rpt64_to_rpt32(nsp_context *ctx, int M, const long long *d_rpt64, long long nnz, int *d_rpt32)

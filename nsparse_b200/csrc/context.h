@@ -24,6 +24,7 @@ struct nsp_spgemm_state {
     int lanes_per_brow = 32;
     bool symbolic_done = false;
     long long b_nnz = 0;          // nnz(B) = B.rpt[K], read back by the symbolic plan
+    bool has_multi_slab = true;   // some row of A has more than 1024 entries (second launch of the heavy numeric kernel)
     bool b_sorted = true;         // rows of B column-sorted (checked by the symbolic plan)
 };
 
@@ -146,7 +147,7 @@ int spgemm_symbolic(nsp_context *ctx, int M, int K, int N, const int *a_rpt, con
 template <typename real>
 int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, const int *a_col,
                    const real *a_val, const int *b_rpt, const int *b_col, const real *b_val,
-                   const long long *c_rpt64, int *c_col, real *c_val);
+                   const long long *c_rpt64, int *c_col, real *c_val, int row0 = 0, int nrows = -1);
 int rpt64_to_rpt32(nsp_context *ctx, int M, const long long *rpt64, long long nnz, int *rpt32);
 
 }  // namespace nsp

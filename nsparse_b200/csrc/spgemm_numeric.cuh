@@ -170,7 +170,12 @@ __device__ __forceinline__ int select32(unsigned x, int n)
 // kSorted: the rows of B are column-sorted (checked once per call on the device); otherwise -- the
 // reference reader leaves the rows of symmetric files unsorted (nsparse.cu:115-123) -- every pass walks
 // the whole B rows and filters by column range.
-template <typename real, int BS, bool kSorted>
+// kPeers: the fused allgatherv variant (multi-GPU, see PeerOut); a separate instantiation so that the
+// single-GPU kernel carries none of its code (with a run-time test only, the mere presence of the peer
+// loops cost the single-GPU kernel 25 % -- register allocation of the hot loops).
+// kMulti: the instantiation for the rows with more than BS entries of A (red.global mode); the other one
+// skips them and vice versa -- two launches over the same class, so that neither carries the other's code.
+template <typename real, int BS, bool kSorted, bool kPeers, bool kMulti>
 __global__ void __launch_bounds__(BS, 1)
 num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                   const real *__restrict__ a_val, const int *__restrict__ b_rpt,
@@ -227,7 +232,11 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
         const int rid = row_perm[lo + r];
         const int a_beg = a_rpt[rid], a_end = a_rpt[rid + 1];
         const int E = a_end - a_beg;
-        const bool one_slab = E <= BS;
+        if ((E > BS) != kMulti) {                  // the other launch's row (CTA uniform)
+            __syncthreads();                       // everyone has read s_row before thread 0 claims again
+            continue;
+        }
+        constexpr bool one_slab = !kMulti;
         const int glog = entry_group_log(E, BS);
         long long out = c_rpt[rid];
         for (int win = 0; win < nwin; ++win) {
@@ -368,7 +377,7 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                 PH(8);
                 real *cv = c_val + out + r0;
                 int *cc = c_col + out + r0;
-                if (peer.n == 0) {
+                if (!kPeers) {
                     for (int i = t; i < cnt; i += BS) {
                         const int j = acc_swz(i);
                         cv[i] = acc[j];
@@ -424,12 +433,16 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                     }
                     __syncthreads();
                     int *cc = c_col + out + r0;
-                    const long long g = peer.off + out + r0;
-                    for (int i = t; i < cnt; i += BS) {
-                        const int c = cols[i];
-                        cc[i] = c;
+                    if (!kPeers) {
+                        for (int i = t; i < cnt; i += BS) cc[i] = cols[i];
+                    } else {
+                        const long long g = peer.off + out + r0;
+                        for (int i = t; i < cnt; i += BS) {
+                            const int c = cols[i];
+                            cc[i] = c;
 #pragma unroll 1
-                        for (int p = 0; p < peer.n; ++p) peer.col[p][g + i] = c;
+                            for (int p = 0; p < peer.n; ++p) peer.col[p][g + i] = c;
+                        }
                     }
                     __syncthreads();
                 }
@@ -454,7 +467,7 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                     run_parts<BS, true, real>(t, total, b_col, b_val, s_part, add_red);
                     PH(10);
                 }
-                if (peer.n > 0) {
+                if (kPeers) {
                     // the row is complete once every thread's reds are performed: read it back from L2 and
                     // hand it to the peers (fused allgatherv of the red.global rows)
                     __threadfence();
@@ -567,13 +580,21 @@ static int launch_num_hash(nsp_context *ctx, const char *name, int grid, size_t 
 template <typename real>
 int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, const int *a_col,
                    const real *a_val, const int *b_rpt, const int *b_col, const real *b_val,
-                   const long long *c_rpt64, int *c_col, real *c_val)
+                   const long long *c_rpt64, int *c_col, real *c_val, int row0, int nrows)
 {
     nsp_spgemm_state &sp = ctx->sp;
     if (!sp.symbolic_done || sp.M != M || sp.K != K || sp.N != N)
         return ctx->fail(-2, "nsp_spgemm_numeric: call nsp_spgemm_symbolic on the same context and shapes first");
+    if (nrows < 0) nrows = M - row0;
+    if (row0 < 0 || nrows < 0 || row0 + nrows > M) return ctx->fail(-2, "nsp_spgemm_numeric: bad row range");
+    // Rows [row0, row0 + nrows) only (the multi-GPU pipeline computes a block in pieces so that finished
+    // pieces travel to the peers while the next one is computed): every per-row array is entered at row0,
+    // row ids are then relative to it, and the row pointers keep indexing the full col / val arrays.
+    a_rpt += row0;
+    c_rpt64 += row0;
+    M = nrows;
     if (M == 0) return 0;
-    if (plan_by_count(ctx, M, kNumShift, a_rpt) != 0) return -1;
+    if (plan_by_count(ctx, M, kNumShift, a_rpt, row0) != 0) return -1;
 
     // ---- class ladder (numeric shift 4: bin b holds 2^(3+b) < nnz <= 2^(4+b)) ----
     //   bin 0          <= 16        4 threads / row, 32 slots
@@ -611,15 +632,27 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
             return ctx->fail(-4, "nsp_spgemm_numeric: shared memory too small for the bitmap kernel");
         const size_t smem = fixed + (size_t)cap * (sizeof(real) + sizeof(int));
         const int grid = num_imin(num_rows_in(sp, bm_bin, kNumBins - 1), (long long)sms);
-        auto kern = sp.b_sorted ? num_bitmap_kernel<real, 1024, true> : num_bitmap_kernel<real, 1024, false>;
-        NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        num_prof_class(ctx, "num_bitmap", bm_bin, kNumBins - 1);
-        kern<<<grid, 1024, smem, ctx->stream>>>(NSP_NUM_ARGS, bm_bin, kNumBins - 1, 4, N, wshift, cap,
-                                                b_vec_end_of(ctx, b_col), (int)ctx->opt_debug,
-                                                ctx->opt_phase_timing ? ctx->phase_cycles() : nullptr, ctx->peer_out);
-        ctx->prof_end();
-        ctx->launches += 1;
-        NSP_CUDA_TRY(ctx, cudaGetLastError());
+        const bool peers = ctx->peer_out.n > 0;
+        // [multi][peers][sorted]
+        void (*kerns[2][2][2])(const int *, const int *, const real *, const int *, const int *, const real *,
+                               const long long *, int *, real *, const int *, int *, int, int, int, int, int, int, int,
+                               int, long long *, const PeerOut) = {
+            {{num_bitmap_kernel<real, 1024, false, false, false>, num_bitmap_kernel<real, 1024, true, false, false>},
+             {num_bitmap_kernel<real, 1024, false, true, false>, num_bitmap_kernel<real, 1024, true, true, false>}},
+            {{num_bitmap_kernel<real, 1024, false, false, true>, num_bitmap_kernel<real, 1024, true, false, true>},
+             {num_bitmap_kernel<real, 1024, false, true, true>, num_bitmap_kernel<real, 1024, true, true, true>}}};
+        for (int multi = 1; multi >= 0; --multi) {          // the long rows first
+            if (multi && !sp.has_multi_slab) continue;
+            auto kern = kerns[multi][peers ? 1 : 0][sp.b_sorted ? 1 : 0];
+            NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            num_prof_class(ctx, multi ? "num_bitmap_long" : "num_bitmap", bm_bin, kNumBins - 1);
+            kern<<<grid, 1024, smem, ctx->stream>>>(NSP_NUM_ARGS, bm_bin, kNumBins - 1, multi ? 5 : 4, N, wshift, cap,
+                                                    b_vec_end_of(ctx, b_col), (int)ctx->opt_debug,
+                                                    ctx->opt_phase_timing ? ctx->phase_cycles() : nullptr, ctx->peer_out);
+            ctx->prof_end();
+            ctx->launches += 1;
+            NSP_CUDA_TRY(ctx, cudaGetLastError());
+        }
     }
     if (bm_bin > 8 && num_rows_in(sp, 8, num_imin(9, bm_bin - 1)) > 0) {
         const int hi = num_imin(9, bm_bin - 1);

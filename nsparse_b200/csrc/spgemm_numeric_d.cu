@@ -3,5 +3,5 @@
 namespace nsp {
 template int spgemm_numeric<double>(nsp_context *, int, int, int, const int *, const int *, const double *,
                                     const int *, const int *, const double *, const long long *, int *,
-                                    double *);
+                                    double *, int, int);
 }

@@ -3,5 +3,5 @@
 namespace nsp {
 template int spgemm_numeric<float>(nsp_context *, int, int, int, const int *, const int *, const float *,
                                    const int *, const int *, const float *, const long long *, int *,
-                                   float *);
+                                   float *, int, int);
 }

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256)
 count_ip_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                 const int *__restrict__ b_rpt, int M, int cap, int shift, int *__restrict__ row_ip,
                 int *__restrict__ hist, unsigned long long *__restrict__ binsum,
-                unsigned long long *__restrict__ total_ip)
+                unsigned long long *__restrict__ total_ip, unsigned long long *__restrict__ max_len = nullptr)
 {
     __shared__ int s_hist[kNumBins];
     __shared__ unsigned long long s_ipsum[kNumBins], s_lensum[kNumBins];
@@ -85,6 +85,12 @@ count_ip_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
     }
     const long long wsum = warp_sum_ll(ip);
     if (lane == 0 && wsum) atomicAdd(&s_total, (unsigned long long)wsum);
+    if (max_len) {
+        int ml = len;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ml = max(ml, __shfl_xor_sync(0xffffffffu, ml, o));
+        if (lane == 0 && ml > 1024) atomicMax(max_len, (unsigned long long)ml);
+    }
     __syncthreads();
     if (threadIdx.x < kNumBins && s_hist[threadIdx.x]) {
         atomicAdd(&hist[threadIdx.x], s_hist[threadIdx.x]);
@@ -343,7 +349,8 @@ int plan_by_intprod(nsp_context *ctx, int M, int K, int cap, const int *a_rpt, c
         const int grid = (M + 255) / 256;
         count_ip_kernel<<<grid, 256, 0, st>>>(a_rpt, a_col, b_rpt, M, cap, kSymShift, sp.d_row_ip,
                                               sp.d_bins + kBinHist, sp.d_binsum,
-                                              (unsigned long long *)(sp.d_scalars + kScalarIp));
+                                              (unsigned long long *)(sp.d_scalars + kScalarIp),
+                                              (unsigned long long *)(sp.d_scalars + kScalarMaxLen));
         bin_offsets_kernel<<<1, 32, 0, st>>>(sp.d_bins);
         scatter_rows_kernel<<<grid, 256, 0, st>>>(sp.d_row_ip, M, cap, kSymShift, sp.d_bins, sp.d_row_perm);
         ctx->launches += 3;
@@ -357,22 +364,25 @@ int plan_by_intprod(nsp_context *ctx, int M, int K, int cap, const int *a_rpt, c
     if (plan_fetch(ctx) != 0) return -1;
     sp.b_sorted = sp.h_scalars[kScalarUnsorted] == 0;
     sp.b_nnz = K > 0 && M > 0 ? sp.h_scalars[kScalarNnzB] : 0;
+    sp.has_multi_slab = sp.h_scalars[kScalarMaxLen] > 1024;
     return 0;
 }
 
-int plan_by_count(nsp_context *ctx, int M, int shift, const int *a_rpt)
+// a_rpt is already entered at row0; the per-row arrays of the plan are entered here
+int plan_by_count(nsp_context *ctx, int M, int shift, const int *a_rpt, int row0)
 {
     nsp_spgemm_state &sp = ctx->sp;
     cudaStream_t st = ctx->stream;
+    const int *row_cnt = sp.d_row_cnt + row0;
+    const int *row_ip = sp.d_row_ip + row0;
     NSP_CUDA_TRY(ctx, cudaMemsetAsync(sp.d_bins, 0, sizeof(int) * kBinInts, st));
     NSP_CUDA_TRY(ctx, cudaMemsetAsync(sp.d_binsum, 0, sizeof(unsigned long long) * kSumInts, st));
     if (M > 0) {
         const int grid = (M + 255) / 256;
         int hgrid = grid < ctx->sm_count * 8 ? grid : ctx->sm_count * 8;
-        hist_kernel<<<hgrid, 256, 0, st>>>(sp.d_row_cnt, sp.d_row_ip, a_rpt, M, shift,
-                                          sp.d_bins + kBinHist, sp.d_binsum);
+        hist_kernel<<<hgrid, 256, 0, st>>>(row_cnt, row_ip, a_rpt, M, shift, sp.d_bins + kBinHist, sp.d_binsum);
         bin_offsets_kernel<<<1, 32, 0, st>>>(sp.d_bins);
-        scatter_rows_kernel<<<grid, 256, 0, st>>>(sp.d_row_cnt, M, 0x7fffffff, shift, sp.d_bins, sp.d_row_perm);
+        scatter_rows_kernel<<<grid, 256, 0, st>>>(row_cnt, M, 0x7fffffff, shift, sp.d_bins, sp.d_row_perm);
         ctx->launches += 3;
     }
     NSP_CUDA_TRY(ctx, cudaGetLastError());

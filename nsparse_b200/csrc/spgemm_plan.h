@@ -25,6 +25,7 @@ constexpr int kSumInts = 96;
 constexpr int kScalarIp = 0;     // total intermediate products (uncapped)
 constexpr int kScalarNnz = 1;    // nnz(C)
 constexpr int kScalarNnzB = 3;     // B.rpt[K]
+constexpr int kScalarMaxLen = 4;   // longest row of A
 constexpr int kScalarUnsorted = 2;   // entries of B below their predecessor in the same row
 
 // Bin shifts: symbolic bins rows by min(intermediate products, N) with bin 0 = "<= 32"
@@ -43,7 +44,7 @@ __device__ __forceinline__ void class_range(const int *bins, int bin_lo, int bin
 int plan_reserve(nsp_context *ctx, int M);
 int plan_by_intprod(nsp_context *ctx, int M, int K, int cap, const int *a_rpt, const int *a_col,
                     const int *b_rpt, const int *b_col);
-int plan_by_count(nsp_context *ctx, int M, int shift, const int *a_rpt);
+int plan_by_count(nsp_context *ctx, int M, int shift, const int *a_rpt, int row0 = 0);
 int scan_row_counts(nsp_context *ctx, int M, long long *rpt64);
 
 }  // namespace nsp

@@ -37,7 +37,8 @@ def spgemm_symbolic(a: CSR, b: CSR, ctx: Context | None = None):
     return d_rpt64, int(nnz.value), int(ip.value)
 
 
-def spgemm_numeric(a: CSR, b: CSR, d_rpt64, nnz: int, ctx: Context | None = None, out=None):
+def spgemm_numeric(a: CSR, b: CSR, d_rpt64, nnz: int, ctx: Context | None = None, out=None, rows=None):
+    """rows = (row0, nrows): only that range of rows is computed (the others are left untouched)."""
     import torch
 
     ctx = ctx or default_context(a.d_rpt.device.index)
@@ -50,6 +51,11 @@ def spgemm_numeric(a: CSR, b: CSR, d_rpt64, nnz: int, ctx: Context | None = None
     else:
         d_col, d_val = out
         assert d_col.numel() >= nnz and d_val.numel() >= nnz and d_val.dtype == tdt
+    if rows is not None:
+        fn = ctx.lib.nsp_spgemm_numeric_rows_d if a.dtype == np.float64 else ctx.lib.nsp_spgemm_numeric_rows_s
+        ctx.check(fn(ctx.handle, a.M, a.N, b.N, int(rows[0]), int(rows[1]), _ptr(a.d_rpt), _ptr(a.d_col), _ptr(a.d_val),
+                     _ptr(b.d_rpt), _ptr(b.d_col), _ptr(b.d_val), _ptr(d_rpt64), _ptr(d_col), _ptr(d_val)))
+        return d_col, d_val
     fn = ctx.lib.nsp_spgemm_numeric_d if a.dtype == np.float64 else ctx.lib.nsp_spgemm_numeric_s
     ctx.check(fn(ctx.handle, a.M, a.N, b.N, _ptr(a.d_rpt), _ptr(a.d_col), _ptr(a.d_val),
                  _ptr(b.d_rpt), _ptr(b.d_col), _ptr(b.d_val), _ptr(d_rpt64), _ptr(d_col), _ptr(d_val)))

@@ -23,9 +23,10 @@ for dtype in (np.float32, np.float64):
     r_rpt, r_col, r_val = ref.to_host()
     cuts, total_ip = ns.partition_rows_by_ip(a.rpt, a.col, a.rpt, world)
     a_loc = ns.row_block(a, cuts[rank], cuts[rank + 1]).memcpy(local)
-    peers = ns.PeerBuffers(ctx, fused=False)
+    peers = ns.PeerBuffers(ctx, pieces=0)
     fused = ns.PeerBuffers(ctx, fused=True)
-    for mode, p in (("push", peers), ("nccl", None), ("fused", fused), ("fused again", fused)):
+    piped = ns.PeerBuffers(ctx, pieces=5)
+    for mode, p in (("push", peers), ("nccl", None), ("fused", fused), ("pipelined", piped), ("pipelined again", piped)):
         c = ns.spgemm_kernel_hash_mgpu(a_loc, a, cuts, a.M, total_ip, ctx, peers=p)
         g_rpt, g_col, g_val = c.to_host()
         ok = c.nnz == ref.nnz and np.array_equal(g_rpt, r_rpt) and np.array_equal(g_col, r_col) and np.array_equal(g_val, r_val)
