@@ -44,6 +44,12 @@ int context_create(nsp_context **out, int device)
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
     ctx->stream = nullptr;
+    if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        delete ctx;
+        return -1;
+    }
     *out = ctx;
     return 0;
 }
@@ -53,6 +59,12 @@ int context_destroy(nsp_context *ctx)
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->aux_stream) {
+        cudaStreamSynchronize(ctx->aux_stream);
+        cudaStreamDestroy(ctx->aux_stream);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->sp.h_scalars) cudaFreeHost(ctx->sp.h_scalars);
     if (ctx->sp.h_bins) cudaFreeHost(ctx->sp.h_bins);

@@ -24,6 +24,7 @@ struct nsp_spgemm_state {
     int lanes_per_brow = 32;
     bool symbolic_done = false;
     long long b_nnz = 0;          // nnz(B) = B.rpt[K], read back by the symbolic plan
+    bool join_pending = false;    // the side-stream launch of this phase has not been joined yet
     bool has_multi_slab = true;   // some row of A has more than 1024 entries (second launch of the heavy numeric kernel)
     bool b_sorted = true;         // rows of B column-sorted (checked by the symbolic plan)
 };
@@ -53,6 +54,10 @@ struct nsp_prof_rec {
 struct nsp_context {
     int device = 0;
     cudaStream_t stream = nullptr;   // nullptr = legacy default stream
+    // side stream + events for the launch that runs next to the main row-class kernels (the long rows of the
+    // heavy numeric class); forked from / joined into `stream`, so callers still see one stream
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int sm_count = 148;
     int max_smem_optin = nsp::kMaxSmemOptin;
     size_t l2_bytes = 0;
@@ -68,6 +73,7 @@ struct nsp_context {
     long long opt_sym_window_shift = 0;  // log2 of the symbolic bitmap window (0: default 20)
     long long opt_num_window_shift = 0;  // log2 of the numeric bitmap window (0: default 19)
     long long opt_num_cap = 0;           // > 0: upper limit of the accumulator chunk (tests)
+    long long opt_no_fork = 0;           // 1: the long rows of the heavy numeric class run on the main stream
     long long opt_no_vec = 0;            // 1: never read B.col with 128-bit loads (tests)
     long long opt_phase_timing = 0;      // 1: the heavy numeric kernel accumulates cycles per phase (development)
     long long *d_phase = nullptr;
@@ -92,9 +98,12 @@ struct nsp_context {
     // per-launch CUDA-event timing of the row-class kernels (nsp_set_option("profile", 1))
     bool profile = false;
     std::vector<nsp_prof_rec> prof;
+    cudaStream_t prof_stream = nullptr;
+    bool prof_on_aux = false;
     void prof_begin(const char *name, long long rows, long long ip, long long alen, long long out = 0)
     {
         if (!profile) return;
+        const cudaStream_t stream = prof_on_aux ? aux_stream : this->stream;
         nsp_prof_rec r;
         r.name = name;
         r.rows = rows;
@@ -109,7 +118,7 @@ struct nsp_context {
     void prof_end()
     {
         if (!profile || prof.empty()) return;
-        cudaEventRecord(prof.back().e1, stream);
+        cudaEventRecord(prof.back().e1, prof_on_aux ? aux_stream : stream);
     }
 
     int fail(int code, const std::string &msg)

@@ -641,18 +641,33 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
              {num_bitmap_kernel<real, 1024, false, true, false>, num_bitmap_kernel<real, 1024, true, true, false>}},
             {{num_bitmap_kernel<real, 1024, false, false, true>, num_bitmap_kernel<real, 1024, true, false, true>},
              {num_bitmap_kernel<real, 1024, false, true, true>, num_bitmap_kernel<real, 1024, true, true, true>}}};
-        for (int multi = 1; multi >= 0; --multi) {          // the long rows first
+        // The long rows (few, each with millions of products: a tail of a handful of CTAs) go to a side stream
+        // and start first; as their CTAs retire, the SMs pick up the CTAs of the main launch, whose dynamic row
+        // queue balances whatever number of them is running.  Joined at the end of the phase.
+        bool forked = false;
+        for (int multi = 1; multi >= 0; --multi) {
             if (multi && !sp.has_multi_slab) continue;
             auto kern = kerns[multi][peers ? 1 : 0][sp.b_sorted ? 1 : 0];
             NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cudaStream_t st = ctx->stream;
+            if (multi && !ctx->opt_no_fork) {
+                NSP_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+                NSP_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+                st = ctx->aux_stream;
+                forked = true;
+            }
+            ctx->prof_on_aux = st != ctx->stream;
             num_prof_class(ctx, multi ? "num_bitmap_long" : "num_bitmap", bm_bin, kNumBins - 1);
-            kern<<<grid, 1024, smem, ctx->stream>>>(NSP_NUM_ARGS, bm_bin, kNumBins - 1, multi ? 5 : 4, N, wshift, cap,
-                                                    b_vec_end_of(ctx, b_col), (int)ctx->opt_debug,
-                                                    ctx->opt_phase_timing ? ctx->phase_cycles() : nullptr, ctx->peer_out);
+            kern<<<grid, 1024, smem, st>>>(NSP_NUM_ARGS, bm_bin, kNumBins - 1, multi ? 5 : 4, N, wshift, cap,
+                                           b_vec_end_of(ctx, b_col), (int)ctx->opt_debug,
+                                           ctx->opt_phase_timing ? ctx->phase_cycles() : nullptr, ctx->peer_out);
             ctx->prof_end();
+            ctx->prof_on_aux = false;
             ctx->launches += 1;
             NSP_CUDA_TRY(ctx, cudaGetLastError());
         }
+        if (forked) NSP_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+        sp.join_pending = forked;
     }
     if (bm_bin > 8 && num_rows_in(sp, 8, num_imin(9, bm_bin - 1)) > 0) {
         const int hi = num_imin(9, bm_bin - 1);
@@ -687,6 +702,10 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
         ctx->prof_end();
         ctx->launches += 1;
         NSP_CUDA_TRY(ctx, cudaGetLastError());
+    }
+    if (sp.join_pending) {
+        NSP_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        sp.join_pending = false;
     }
     if (ctx->peer_out.n > 0) {
         // rows the heavy kernel did not push itself: the light classes and the multi-slab rows
