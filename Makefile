@@ -13,7 +13,7 @@ LIBDIR    := nsparse_b200/lib
 BIN       := bin
 
 CORE_CU   := context spgemm_plan spgemm_symbolic spgemm_numeric_s spgemm_numeric_d c_api amb_convert amb_spmv amb_api
-CORE_OBJ  := $(addprefix $(OBJ)/,$(addsuffix .o,$(CORE_CU))) $(OBJ)/gen.o
+CORE_OBJ  := $(addprefix $(OBJ)/,$(addsuffix .o,$(CORE_CU))) $(OBJ)/gen.o $(OBJ)/mtx_reader.o
 
 .PHONY: all lib compat drivers clean oracle
 all: lib compat oracle
@@ -27,6 +27,10 @@ $(OBJ)/%.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h $(SRC)/*.cuh include/*.h)
 $(OBJ)/gen.o: $(SRC)/gen.cpp include/nsparse_b200.h
 	@mkdir -p $(OBJ)
 	$(CXX) -O3 -fPIC -fopenmp -Iinclude -c $< -o $@
+
+$(OBJ)/mtx_reader.o: $(SRC)/mtx_reader.cpp include/nsparse_b200.h
+	@mkdir -p $(OBJ)
+	$(CXX) -O3 -std=c++17 -fPIC -fopenmp -Iinclude -c $< -o $@
 
 $(LIBDIR)/libnsparse_b200.so: $(CORE_OBJ)
 	@mkdir -p $(LIBDIR)

@@ -469,6 +469,11 @@ def run_spmv(args, ctx, peak, peak_src):
     t0 = time.perf_counter()
     amb = ns.csr2amb(lap, ctx=ctx)
     torch.cuda.synchronize()
+    conv_first_s = time.perf_counter() - t0      # includes lazy kernel loading and the first growth of the arena
+    del amb
+    t0 = time.perf_counter()
+    amb = ns.csr2amb(lap, ctx=ctx)
+    torch.cuda.synchronize()
     conv_s = time.perf_counter() - t0
     y = torch.empty(lap.M, dtype=torch.float64, device="cuda")
     for _ in range(5):
@@ -487,7 +492,7 @@ def run_spmv(args, ctx, peak, peak_src):
     return {"metric": "AMB SpMV GFLOPS", "value": 2.0 * lap.nnz / ms / 1e6, "unit": "GFLOPS", "ms": ms,
             "GBs_alg": alg / ms / 1e6, "roofline_frac": alg / ms / 1e6 / peak, "peak_source": peak_src,
             "workload": f"5-pt Laplacian {n}^2 fp64, nnz={lap.nnz}", "seg_size": amb.seg_size,
-            "block_size": amb.block_size, "conversion_s": conv_s, "launches": ctx.launches - l0,
+            "block_size": amb.block_size, "conversion_s": conv_s, "conversion_first_call_s": conv_first_s, "launches": ctx.launches - l0,
             "l2_policy": "matrix values (>= 670 MB) >> L2"}
 
 

@@ -213,6 +213,18 @@ int nsp_spmv_amb_host_d(nsp_context *ctx, const nsp_amb *mat, const double *h_x,
 int nsp_memcpy_d2h(nsp_context *ctx, void *h_dst, const void *d_src, size_t bytes);
 
 /* ------------------------------------------------------------------------------------
+ * MatrixMarket coordinate file -> host CSR, parsed in parallel (OpenMP).  flags == 0 reproduces the
+ * reference reader convert_file_csr (nsparse.cu:14-136) entry for entry: "general" in the banner or
+ * off-diagonals mirrored right after the original, file order inside every row, nothing sorted or merged,
+ * missing value = 1, at most `nz` entries.  NSP_MTX_SORT_MERGE orders every row by column and sums
+ * duplicates.  The arrays are malloc'ed (free() or nsp_free_host); val is float* or double*.
+ * ---------------------------------------------------------------------------------- */
+#define NSP_MTX_SORT_MERGE 1
+int nsp_read_mtx(const char *path, int is_double, int flags, int *M, int *N, long long *nnz, int *nnz_max,
+                 int **h_rpt, int **h_col, void **h_val);
+void nsp_free_host(void *p);
+
+/* ------------------------------------------------------------------------------------
  * synthetic inputs (host side, OpenMP; counter-based so every rank and the numpy mirror
  * in nsparse_b200/gen.py produce identical edges)
  * ---------------------------------------------------------------------------------- */

@@ -74,6 +74,9 @@ SIGNATURES = {
     "nsp_spgemm_set_peers": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), ll]),
     "nsp_push_multicast": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t]),
     "nsp_push_to_peers": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.c_size_t, vp, C.c_size_t]),
+    "nsp_read_mtx": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(ll),
+                               C.POINTER(C.c_int), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "nsp_free_host": (None, [vp]),
     "nsp_gen_rmat_edges": (C.c_int, [C.c_int, ll, C.c_ulonglong, vp, vp]),
 }
 

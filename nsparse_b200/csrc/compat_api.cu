@@ -68,81 +68,18 @@ void init_csr_matrix_from_file(sfCSR *mat, char *file_name)
         printf("Cannot find file\n");
         exit(1);
     }
-    printf("Read mtx file: %s\n", file_name);
-    std::vector<char> buf(1 << 16);
-    char *line = buf.data();
-    const int cap = (int)buf.size();
-    bool general = false;
-    if (fgets(line, cap, fp)) general = strstr(line, "general") != nullptr;
-    do {
-        if (!fgets(line, cap, fp)) {
-            printf("Cannot read the size line\n");
-            exit(1);
-        }
-    } while (line[0] == '%');
-    int M = 0, N = 0, nz = 0;
-    if (sscanf(line, "%d %d %d", &M, &N, &nz) != 3 || M < 0 || N < 0 || nz < 0) {
-        printf("Cannot read the size line\n");
-        exit(1);
-    }
-    std::vector<int> er, ec;
-    std::vector<real> ev;
-    er.reserve((size_t)nz * (general ? 1 : 2));
-    ec.reserve(er.capacity());
-    ev.reserve(er.capacity());
-    std::vector<int> cnt((size_t)M + 1, 0);
-    int seen = 0;
-    while (seen < nz && fgets(line, cap, fp)) {
-        char *p = line, *q = nullptr;
-        const long r = strtol(p, &q, 10);
-        if (q == p) continue;   // blank / malformed line
-        p = q;
-        const long c = strtol(p, &q, 10);
-        if (q == p) continue;
-        p = q;
-        real v = (real)strtod(p, &q);
-        if (q == p) v = (real)1;
-        ++seen;
-        if (r < 1 || r > M || c < 1 || c > N) {
-            printf("entry (%ld,%ld) outside the %d x %d matrix\n", r, c, M, N);
-            exit(1);
-        }
-        er.push_back((int)r - 1);
-        ec.push_back((int)c - 1);
-        ev.push_back(v);
-        cnt[r - 1]++;
-        if (!general && r != c) {
-            if (c > M || r > N) {
-                printf("symmetric file with a non-square shape\n");
-                exit(1);
-            }
-            er.push_back((int)c - 1);
-            ec.push_back((int)r - 1);
-            ev.push_back(v);
-            cnt[c - 1]++;
-        }
-    }
     fclose(fp);
-    const size_t nnz = er.size();
-    if (nnz > (size_t)INT_MAX) {
-        printf("more than 2^31 entries\n");
+    printf("Read mtx file: %s\n", file_name);
+    // parallel parse, entry-for-entry the reference reader's result (csrc/mtx_reader.cpp)
+    int M = 0, N = 0, nnz_max = 0;
+    long long nnz = 0;
+    void *val = nullptr;
+    const int rc = nsp_read_mtx(file_name, sizeof(real) == 8, 0, &M, &N, &nnz, &nnz_max, &mat->rpt, &mat->col, &val);
+    if (rc != 0) {
+        printf("Cannot read the matrix (nsp_read_mtx: %d)\n", rc);
         exit(1);
     }
-    mat->rpt = (int *)malloc(sizeof(int) * ((size_t)M + 1));
-    mat->col = (int *)malloc(sizeof(int) * (nnz ? nnz : 1));
-    mat->val = (real *)malloc(sizeof(real) * (nnz ? nnz : 1));
-    int nnz_max = 0;
-    mat->rpt[0] = 0;
-    for (int i = 0; i < M; ++i) {
-        mat->rpt[i + 1] = mat->rpt[i] + cnt[i];
-        if (cnt[i] > nnz_max) nnz_max = cnt[i];
-    }
-    std::vector<int> cur(mat->rpt, mat->rpt + M);
-    for (size_t e = 0; e < nnz; ++e) {
-        const int at = cur[er[e]]++;
-        mat->col[at] = ec[e];
-        mat->val[at] = ev[e];
-    }
+    mat->val = (real *)val;
     mat->M = M;
     mat->N = N;
     mat->nnz = (int)nnz;
