@@ -47,7 +47,10 @@ const char *nsp_last_error(nsp_context *ctx);
 /* stream == NULL selects the legacy default stream (what the sample drivers time on). */
 int nsp_set_stream(nsp_context *ctx, void *cuda_stream);
 int nsp_sync(nsp_context *ctx);
-/* tuning knobs, mostly for tests: name in {"sym_bitmap_min", "num_bitmap_min", "lanes_per_brow"} */
+/* tuning knobs, mostly for tests and measurements: "sym_bitmap_min" / "num_bitmap_min" (rows above this many
+ * products / entries take the bitmap kernels), "sym_window_shift" / "num_window_shift" (log2 of the bitmap window),
+ * "num_cap" (upper limit of the accumulator chunk), "no_vec" (no 128-bit loads of B.col), "no_fork" (long rows on
+ * the main stream), "profile", "debug", "phase_timing" */
 int nsp_set_option(nsp_context *ctx, const char *name, long long value);
 /* With option "profile" = 1 every row-class kernel launch is bracketed by CUDA events on the
  * context's stream.  nsp_profile_dump syncs, writes one line per launch

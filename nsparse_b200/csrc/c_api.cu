@@ -62,11 +62,7 @@ int nsp_set_option(nsp_context *ctx, const char *name, long long value)
     }
     else if (!strcmp(name, "sym_window_shift")) ctx->opt_sym_window_shift = value;
     else if (!strcmp(name, "num_window_shift")) ctx->opt_num_window_shift = value;
-    else if (!strcmp(name, "lanes_per_brow")) {
-        if (value != 0 && value != 4 && value != 8 && value != 16 && value != 32)
-            return ctx->fail(NSP_ERR_ARG, "lanes_per_brow must be 0, 4, 8, 16 or 32");
-        ctx->opt_lanes_per_brow = value;
-    } else
+    else
         return ctx->fail(NSP_ERR_ARG, std::string("unknown option ") + name);
     return 0;
 }

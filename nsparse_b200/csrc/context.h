@@ -21,7 +21,6 @@ struct nsp_spgemm_state {
     long long *d_scalars = nullptr;   // [8]  total ip, nnz, ...
     long long *d_scan_tmp = nullptr;  // block sums of the row-pointer scan
     long long *h_scalars = nullptr;   // pinned mirror
-    int lanes_per_brow = 32;
     bool symbolic_done = false;
     long long b_nnz = 0;          // nnz(B) = B.rpt[K], read back by the symbolic plan
     bool join_pending = false;    // the side-stream launch of this phase has not been joined yet
@@ -86,7 +85,6 @@ struct nsp_context {
         return d_phase;
     }
     long long opt_debug = 0;             // development only: bit 0 skip emit, 1 skip value pass, 2 skip zero-fill
-    long long opt_lanes_per_brow = 0;    // 0: pick from nnz(B)/K
 
     nsp_spgemm_state sp;
     nsp::PeerOut peer_out;   // nsp_spgemm_set_peers

@@ -189,37 +189,6 @@ __device__ __forceinline__ int scan_parts(int t, int kb, int len, PartScratch<BS
     return s.pre[BS];
 }
 
-// Stage the slab [base, base + BS) of the A row: B-row starts / lengths / a_ij and the part prefix.
-template <int BS, bool kLoadVal, typename real>
-__device__ __forceinline__ int stage_parts(int t, int base, int a_end, const int *__restrict__ a_col,
-                                           const real *__restrict__ a_val, const int *__restrict__ b_rpt,
-                                           PartScratch<BS, real> &s)
-{
-    int len = 0, kb = 0;
-    if (base + t < a_end) {
-        const int ac = ld_stream(a_col + base + t);
-        kb = ld_nc(b_rpt + ac);
-        len = ld_nc(b_rpt + ac + 1) - kb;
-        if (kLoadVal) s.av[t] = ld_stream(a_val + base + t);
-    }
-    s.kb[t] = kb;
-    s.len[t] = len;
-    return scan_parts<BS, real>(t, kb, len, s);
-}
-
-// first k in [lo, hi) with b_col[k] >= key (B rows are column-sorted)
-__device__ __forceinline__ int lower_bound_col(const int *__restrict__ b_col, int lo, int hi, int key)
-{
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (ld_nc(b_col + mid) < key)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    return lo;
-}
-
 // stage_parts restricted to the products whose column lies in [col_lo, col_hi): the heavy kernels
 // walk a row of C in ascending column ranges (bitmap windows, accumulator chunks) and every product
 // is visited once per pass because the sub-range of each B row is found by binary search instead of

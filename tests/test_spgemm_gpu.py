@@ -160,23 +160,21 @@ def test_numeric_bin_boundaries(ns, ctx, nnz_row):
     assert got[0].tolist() == [0, nnz_row, nnz_row + 1]
 
 
-@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_all_lane_widths_and_forced_bitmap(ns, dtype, lanes):
-    """Every lanes-per-B-row instantiation, with the bitmap kernels forced on for all rows above
-    the 4-thread class, must agree with the hash kernels and the oracle."""
+def test_forced_bitmap_agrees_with_hash_classes(ns, dtype):
+    """The bitmap kernels forced on for all rows above the 4-thread class must agree with the hash kernels
+    and the oracle."""
     a = _rand(ns, 1500, 1200, 0.02, 21, dtype)
     b = _rand(ns, 1200, 5000, 0.01, 22, dtype)
     want = _oracle(a, b)
     for force in (False, True):
         c2 = ns.Context(0)
-        c2.set_option("lanes_per_brow", lanes)
         if force:
             c2.set_option("sym_bitmap_min", 32)
             c2.set_option("num_bitmap_min", 16)
         _, got = _run(ns, c2, a, b)
         ok, msg = oracle.check_spgemm_answer(got, want)
-        assert ok, f"lanes={lanes} force_bitmap={force}: {msg}"
+        assert ok, f"force_bitmap={force}: {msg}"
         assert np.array_equal(got[2], want[2])
         c2.close()
 
