@@ -50,6 +50,20 @@ int context_create(nsp_context **out, int device)
         delete ctx;
         return -1;
     }
+    {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&ctx->mem_pool, &props) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(ctx->mem_pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            ctx->mem_pool = nullptr;       // fall back to the device's default pool
+            cudaGetLastError();
+        }
+    }
     *out = ctx;
     return 0;
 }
@@ -63,6 +77,7 @@ int context_destroy(nsp_context *ctx)
         cudaStreamSynchronize(ctx->aux_stream);
         cudaStreamDestroy(ctx->aux_stream);
     }
+    if (ctx->mem_pool) cudaMemPoolDestroy(ctx->mem_pool);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->arena) cudaFree(ctx->arena);

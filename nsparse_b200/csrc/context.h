@@ -57,6 +57,7 @@ struct nsp_context {
     // heavy numeric class); forked from / joined into `stream`, so callers still see one stream
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaMemPool_t mem_pool = nullptr;   // stream-ordered pool of the AMB conversion's temporaries (kept between calls)
     int sm_count = 148;
     int max_smem_optin = nsp::kMaxSmemOptin;
     size_t l2_bytes = 0;
