@@ -127,3 +127,31 @@ def test_numeric_rerun_with_new_values(ns, dtype):
     assert np.array_equal(col2[:nnz].cpu().numpy(), want2[1]) and np.array_equal(col1[:nnz].cpu().numpy(), want2[1])
     assert np.array_equal(val2[:nnz].cpu().numpy(), want2[2])
     ctx.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_numeric_by_row_ranges(ns, dtype):
+    """nsp_spgemm_numeric_rows_*: the numeric phase piece by piece (what the pipelined multi-GPU gather
+    uses) must fill C exactly like one call, and leave the rows outside a piece untouched."""
+    import torch
+
+    from nsparse_b200 import gen
+
+    a = gen.rmat_csr(14, 16, seed=9, dtype=dtype, values="small_int")
+    a.memcpy()
+    ctx = ns.Context(0)
+    d_rpt64, nnz, _ = ns.spgemm_symbolic(a, a, ctx)
+    col0, val0 = ns.spgemm_numeric(a, a, d_rpt64, nnz, ctx)
+    ctx.sync()
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    col = torch.full((nnz,), -7, dtype=torch.int32, device="cuda")
+    val = torch.full((nnz,), -7, dtype=tdt, device="cuda")
+    cuts = [0, 1, a.M // 3, a.M // 3, a.M - 5, a.M]
+    rpt = d_rpt64.cpu().numpy()
+    for r0, r1 in zip(cuts[:-1], cuts[1:]):
+        ns.spgemm_numeric(a, a, d_rpt64, nnz, ctx, out=(col, val), rows=(r0, r1 - r0))
+        ctx.sync()
+        done = int(rpt[r1])
+        assert torch.equal(col[:done], col0[:done]) and torch.equal(val[:done], val0[:done])
+        assert bool((col[done:] == -7).all())
+    ctx.close()
