@@ -187,6 +187,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if "TORCHELASTIC_RUN_ID" in os.environ or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # torchrun pins OMP_NUM_THREADS=1 for its workers; the reference arm is ONE process on all host cores
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     dtype = np.float32
     a = make_rmat(args.scale, args.ef, dtype)
     r = cpu_spgemm_sample(a, target_s=args.cpu_seconds, steps=args.steps, warmup=min(args.warmup, 1))
@@ -358,6 +361,8 @@ def run_ours(args):
     if not args.no_e2e:
         del c
         state.clear()
+        if peers is not None:
+            peers.release()                # the gathered copies of C (78 GB per rank at scale 20) are not needed any more
         torch.cuda.empty_cache()
         e2e = run_e2e(args, ctx, a, a_loc, world, rank, dev, ip)
 
