@@ -9,12 +9,12 @@
 //   * the whole table is sorted bitonically with the free slots (key 0xffffffff) sinking to the
 //     end, which replaces the global-atomic compaction (:904-912) AND the O(nnz^2) counting sort
 //     (:917-925) with O(n log^2 n) shared-memory work and no global atomics;
-//   * rows above the hash ladder (reference: each_gl with 2*max_nz global slots PER ROW and an
-//     O(nnz^2) sort in global memory, :929-1027) use a column-tile BITMAP + RANK scheme: pass 1
-//     marks the row's columns in a shared-memory bitmap, a CTA-wide scan turns it into ranks,
-//     C.col is emitted straight from the bitmap (already sorted), pass 2 adds every product into
-//     C.val[rpt + rank(col)] with red.global.add.  No table, no compaction, no sort, no workspace;
-//   * native fp64 atomics everywhere (reference SpMV/SpGEMM fall back to CAS loops on fp64).
+//   * rows above ~2048 entries (reference: each_gl with 2*max_nz global slots PER ROW and an O(nnz^2) sort
+//     in global memory, :929-1027) use a column-window BITMAP + RANK scheme with accumulators in shared
+//     memory: the row's columns are marked in a bitmap, a sweep turns it into ranks, the products are added
+//     at acc[rank] with shared-memory atomics chunk by chunk and written out with coalesced stores; no
+//     table, no compaction, no sort, no workspace (num_bitmap_kernel below);
+//   * native fp64 atomics everywhere (reference SpMV/SpGEMM fall back to CAS loops on fp64 in global memory).
 #pragma once
 
 #include "context.h"
