@@ -430,9 +430,14 @@ def run_e2e(args, ctx, a, a_loc, world, rank, dev, ip):
     csum, nbytes = C.c_ulonglong(), C.c_longlong()
 
     def one():
-        ctx.check(L.nsp_spgemm_host_s(ctx.handle, a_loc.M, a.M, a.N, p(ha[0]), p(ha[1]), p(ha[2]), p(hb[0]),
-                                      p(hb[1]), p(hb[2]), C.byref(nnz)))
-        ctx.check(L.nsp_spgemm_host_drain(ctx.handle, p(stage), stage.numel(), C.byref(csum), C.byref(nbytes)))
+        if args.e2e_pieces > 0:
+            ctx.check(L.nsp_spgemm_host_stream_s(ctx.handle, a_loc.M, a.M, a.N, p(ha[0]), p(ha[1]), p(ha[2]), p(hb[0]),
+                                                 p(hb[1]), p(hb[2]), p(stage), stage.numel(), args.e2e_pieces,
+                                                 C.byref(nnz), C.byref(csum), C.byref(nbytes)))
+        else:
+            ctx.check(L.nsp_spgemm_host_s(ctx.handle, a_loc.M, a.M, a.N, p(ha[0]), p(ha[1]), p(ha[2]), p(hb[0]),
+                                          p(hb[1]), p(hb[2]), C.byref(nnz)))
+            ctx.check(L.nsp_spgemm_host_drain(ctx.handle, p(stage), stage.numel(), C.byref(csum), C.byref(nbytes)))
 
     steps = max(1, min(args.steps, args.e2e_steps))
     one()                                   # warm-up (allocates the device buffers)
@@ -457,7 +462,9 @@ def run_e2e(args, ctx, a, a_loc, world, rank, dev, ip):
     ctx.check(L.nsp_spgemm_host_release(ctx.handle))
     return {"value": 2.0 * ip / ms / 1e6, "unit": "GFLOPS", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": int(nbytes.value), "ms_per_step": ms, "steps": steps,
-            "api": "nsp_spgemm_host_s + nsp_spgemm_host_drain (pinned host CSR in, all of C out)"}
+            "api": (f"nsp_spgemm_host_stream_s (pinned host CSR in, all of C out, {args.e2e_pieces} row ranges drained "
+                    "while the next is computed)") if args.e2e_pieces > 0 else
+                   "nsp_spgemm_host_s + nsp_spgemm_host_drain (pinned host CSR in, all of C out)"}
 
 
 def run_spmv(args, ctx, peak, peak_src):
@@ -511,6 +518,7 @@ def main():
     ap.add_argument("--ef", type=int, default=16)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-pieces", type=int, default=0, help="> 0: nsp_spgemm_host_stream_s with that many row ranges (measured: no gain, the D2H is PCIe-bound)")
     ap.add_argument("--spmv-grid", type=int, default=4096)
     ap.add_argument("--gather", default="fused", choices=["pipelined", "fused", "push"],
                     help="N > 1: how a rank's block of C reaches the peers (see nsparse_b200/multi_gpu.py)")

@@ -126,6 +126,20 @@ int nsp_spgemm_host_fetch_d(nsp_context *ctx, long long *h_c_rpt64, int *h_c_col
  * into a 64-bit checksum on the host; for results that do not fit host memory. */
 int nsp_spgemm_host_drain(nsp_context *ctx, void *h_stage, size_t stage_bytes,
                           unsigned long long *h_checksum, long long *h_bytes);
+/* The whole call end to end with overlap: A, B in (pinned) host memory, C streamed to the host through the
+ * pinned staging buffer WHILE it is computed -- the numeric phase runs in `pieces` row ranges of ~equal output
+ * and a second host thread drains every finished range on its own stream (order of the stream: row pointer,
+ * then col and val of each range).  Returns nnz(C), the fold of the drained chunks and the bytes moved. */
+int nsp_spgemm_host_stream_s(nsp_context *ctx, int M, int K, int N,
+                             const int *h_a_rpt, const int *h_a_col, const float *h_a_val,
+                             const int *h_b_rpt, const int *h_b_col, const float *h_b_val,
+                             void *h_stage, size_t stage_bytes, int pieces, long long *h_nnz_c,
+                             unsigned long long *h_checksum, long long *h_bytes);
+int nsp_spgemm_host_stream_d(nsp_context *ctx, int M, int K, int N,
+                             const int *h_a_rpt, const int *h_a_col, const double *h_a_val,
+                             const int *h_b_rpt, const int *h_b_col, const double *h_b_val,
+                             void *h_stage, size_t stage_bytes, int pieces, long long *h_nnz_c,
+                             unsigned long long *h_checksum, long long *h_bytes);
 int nsp_spgemm_host_release(nsp_context *ctx);
 
 /* ------------------------------------------------------------------------------------

@@ -55,6 +55,10 @@ SIGNATURES = {
     "nsp_spgemm_host_fetch_s": (C.c_int, [vp, vp, vp, vp]),
     "nsp_spgemm_host_fetch_d": (C.c_int, [vp, vp, vp, vp]),
     "nsp_spgemm_host_drain": (C.c_int, [vp, vp, C.c_size_t, C.POINTER(C.c_ulonglong), C.POINTER(ll)]),
+    "nsp_spgemm_host_stream_s": (C.c_int, [vp, C.c_int, C.c_int, C.c_int] + [vp] * 6 + [vp, C.c_size_t, C.c_int, C.POINTER(ll),
+                                                                                      C.POINTER(C.c_ulonglong), C.POINTER(ll)]),
+    "nsp_spgemm_host_stream_d": (C.c_int, [vp, C.c_int, C.c_int, C.c_int] + [vp] * 6 + [vp, C.c_size_t, C.c_int, C.POINTER(ll),
+                                                                                      C.POINTER(C.c_ulonglong), C.POINTER(ll)]),
     "nsp_spgemm_host_release": (C.c_int, [vp]),
     "nsp_csr2amb_s": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, ll, C.c_int, C.c_int, vp,
                                 C.POINTER(nsp_amb)]),

@@ -3,6 +3,10 @@
 
 #include <string.h>
 
+#include <atomic>
+#include <thread>
+#include <vector>
+
 #include "context.h"
 
 using nsp::context_create;
@@ -373,10 +377,11 @@ static int upload_csr(nsp_context *ctx, int rows, const int *h_rpt, const int *h
     return 0;
 }
 
+// uploads A and B, symbolic phase, (re)allocation of C on the device; returns the device views of B
 template <typename real>
-static int spgemm_host(nsp_context *ctx, int M, int K, int N, const int *h_a_rpt, const int *h_a_col,
-                       const real *h_a_val, const int *h_b_rpt, const int *h_b_col, const real *h_b_val,
-                       long long *h_nnz_c)
+static int spgemm_host_prepare(nsp_context *ctx, int M, int K, int N, const int *h_a_rpt, const int *h_a_col,
+                               const real *h_a_val, const int *h_b_rpt, const int *h_b_col, const real *h_b_val,
+                               const int *&b_rpt, const int *&b_col, const real *&b_val, long long &nnz)
 {
     if (M < 0 || K < 0 || N < 0 || !h_a_rpt || !h_b_rpt) return ctx->fail(NSP_ERR_ARG, "nsp_spgemm_host: bad argument");
     nsp_host_result &h = ctx->host;
@@ -393,8 +398,9 @@ static int spgemm_host(nsp_context *ctx, int M, int K, int N, const int *h_a_rpt
                          h.a_nnz_cap, a_nnz) != 0)
         return -1;
     h.in_val_bytes = (int)sizeof(real);
-    const int *b_rpt = h.d_a_rpt, *b_col = h.d_a_col;
-    const real *b_val = (const real *)h.d_a_val;
+    b_rpt = h.d_a_rpt;
+    b_col = h.d_a_col;
+    b_val = (const real *)h.d_a_val;
     if (!same) {
         if (upload_csr<real>(ctx, K, h_b_rpt, h_b_col, h_b_val, h.d_b_rpt, h.d_b_col, h.d_b_val, h.b_m_cap,
                              h.b_nnz_cap, b_nnz) != 0)
@@ -409,7 +415,8 @@ static int spgemm_host(nsp_context *ctx, int M, int K, int N, const int *h_a_rpt
         NSP_CUDA_TRY(ctx, cudaMalloc((void **)&h.d_rpt64, sizeof(long long) * ((size_t)M + 1)));
     }
     h.M = M;
-    long long nnz = 0, ip = 0;
+    long long ip = 0;
+    nnz = 0;
     if (nsp::spgemm_symbolic(ctx, M, K, N, h.d_a_rpt, h.d_a_col, b_rpt, b_col, h.d_rpt64, &nnz, &ip) != 0)
         return -1;
     if (nnz > h.nnz || h.val_bytes != (int)sizeof(real) || !h.d_col) {
@@ -422,10 +429,184 @@ static int spgemm_host(nsp_context *ctx, int M, int K, int N, const int *h_a_rpt
     }
     h.nnz = nnz;
     h.val_bytes = (int)sizeof(real);
+    return 0;
+}
+
+template <typename real>
+static int spgemm_host(nsp_context *ctx, int M, int K, int N, const int *h_a_rpt, const int *h_a_col,
+                       const real *h_a_val, const int *h_b_rpt, const int *h_b_col, const real *h_b_val,
+                       long long *h_nnz_c)
+{
+    const int *b_rpt, *b_col;
+    const real *b_val;
+    long long nnz = 0;
+    if (spgemm_host_prepare<real>(ctx, M, K, N, h_a_rpt, h_a_col, h_a_val, h_b_rpt, h_b_col, h_b_val, b_rpt, b_col,
+                                  b_val, nnz) != 0)
+        return -1;
+    nsp_host_result &h = ctx->host;
     if (nsp::spgemm_numeric<real>(ctx, M, K, N, h.d_a_rpt, h.d_a_col, (const real *)h.d_a_val, b_rpt, b_col,
                                   b_val, h.d_rpt64, h.d_col, (real *)h.d_val) != 0)
         return -1;
     if (h_nnz_c) *h_nnz_c = nnz;
+    return 0;
+}
+
+// Double-buffered device -> pinned staging transfer of [src, src + len) on `st`, folded into `sum`.
+struct StagedDrain {
+    unsigned char *stage;
+    size_t half;
+    cudaStream_t st;
+    cudaEvent_t ev[2];
+    bool pending[2] = {false, false};
+    size_t pend_len[2] = {0, 0};
+    int slot = 0;
+    unsigned long long sum = 0;
+    long long total = 0;
+    void consume(int s)
+    {
+        // fold the first and last word of the chunk: proves the bytes arrived without a host pass
+        // over tens of GB
+        cudaEventSynchronize(ev[s]);
+        const unsigned char *p = stage + (size_t)s * half;
+        unsigned long long a = 0, b = 0;
+        memcpy(&a, p, pend_len[s] >= 8 ? 8 : pend_len[s]);
+        if (pend_len[s] >= 8) memcpy(&b, p + pend_len[s] - 8, 8);
+        sum = sum * 1099511628211ull + (a ^ (b << 1));
+        pending[s] = false;
+    }
+    cudaError_t range(const void *src, size_t len)
+    {
+        for (size_t off = 0; off < len; off += half) {
+            const size_t n = len - off < half ? len - off : half;
+            if (pending[slot]) consume(slot);
+            cudaError_t e = cudaMemcpyAsync(stage + (size_t)slot * half, (const unsigned char *)src + off, n,
+                                            cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return e;
+            e = cudaEventRecord(ev[slot], st);
+            if (e != cudaSuccess) return e;
+            pending[slot] = true;
+            pend_len[slot] = n;
+            total += (long long)n;
+            slot ^= 1;
+        }
+        return cudaSuccess;
+    }
+    void finish()
+    {
+        if (pending[slot]) consume(slot);
+        if (pending[slot ^ 1]) consume(slot ^ 1);
+    }
+};
+
+__global__ void find_row_cuts_kernel(const long long *__restrict__ rpt, int M, long long nnz, int pieces,
+                                     int *__restrict__ rows, long long *__restrict__ offs)
+{
+    const int k = threadIdx.x;
+    if (k > pieces) return;
+    int r = M;
+    if (k < pieces) {
+        const long long target = nnz / pieces * k;
+        int lo = 0, hi = M;                       // first row whose start is >= target
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (rpt[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        r = lo;
+    }
+    rows[k] = r;
+    offs[k] = rpt[r];
+}
+
+// spgemm_kernel_hash with HOST buffers END TO END: the numeric phase runs in `pieces` contiguous row ranges
+// of ~equal output and a second host thread streams every finished range to the host through the pinned
+// staging buffer on its own stream, so the PCIe transfer of C (78 GB at R-MAT scale 20, 87 % of the
+// un-overlapped call) hides the compute of the following ranges.
+template <typename real>
+static int spgemm_host_stream(nsp_context *ctx, int M, int K, int N, const int *h_a_rpt, const int *h_a_col,
+                              const real *h_a_val, const int *h_b_rpt, const int *h_b_col, const real *h_b_val,
+                              void *h_stage, size_t stage_bytes, int pieces, long long *h_nnz_c,
+                              unsigned long long *h_checksum, long long *h_bytes)
+{
+    if (!h_stage || stage_bytes < 4096) return ctx->fail(NSP_ERR_ARG, "nsp_spgemm_host_stream: bad staging buffer");
+    if (pieces < 1) pieces = 1;
+    if (pieces > 64) pieces = 64;
+    const int *b_rpt, *b_col;
+    const real *b_val;
+    long long nnz = 0;
+    if (spgemm_host_prepare<real>(ctx, M, K, N, h_a_rpt, h_a_col, h_a_val, h_b_rpt, h_b_col, h_b_val, b_rpt, b_col,
+                                  b_val, nnz) != 0)
+        return -1;
+    nsp_host_result &h = ctx->host;
+    if (M < pieces) pieces = M > 0 ? M : 1;
+    // row cuts of equal output
+    int rows[65];
+    long long offs[65];
+    {
+        int *d_rows = nullptr;
+        long long *d_offs = nullptr;
+        NSP_CUDA_TRY(ctx, cudaMalloc((void **)&d_rows, sizeof(int) * 65));
+        NSP_CUDA_TRY(ctx, cudaMalloc((void **)&d_offs, sizeof(long long) * 65));
+        find_row_cuts_kernel<<<1, 128, 0, ctx->stream>>>(h.d_rpt64, M, nnz, pieces, d_rows, d_offs);
+        ctx->launches += 1;
+        NSP_CUDA_TRY(ctx, cudaMemcpyAsync(rows, d_rows, sizeof(int) * (pieces + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        NSP_CUDA_TRY(ctx, cudaMemcpyAsync(offs, d_offs, sizeof(long long) * (pieces + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        NSP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_rows);
+        cudaFree(d_offs);
+    }
+    cudaStream_t copy_st = nullptr;
+    NSP_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> done((size_t)pieces);
+    for (auto &e : done) NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    StagedDrain dr;
+    dr.stage = (unsigned char *)h_stage;
+    dr.half = (stage_bytes / 2) & ~size_t(255);
+    dr.st = copy_st;
+    NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&dr.ev[0], cudaEventDisableTiming));
+    NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&dr.ev[1], cudaEventDisableTiming));
+    std::atomic<int> launched(0);
+    std::atomic<int> failed(0);
+    cudaError_t drain_err = cudaSuccess;
+    const int device = ctx->device;
+    std::thread drainer([&]() {
+        cudaSetDevice(device);
+        // the row pointer is final after the symbolic phase
+        drain_err = dr.range(h.d_rpt64, sizeof(long long) * ((size_t)M + 1));
+        for (int k = 0; k < pieces && drain_err == cudaSuccess; ++k) {
+            while (launched.load(std::memory_order_acquire) <= k) {
+                if (failed.load()) return;
+                std::this_thread::yield();
+            }
+            drain_err = cudaStreamWaitEvent(copy_st, done[k], 0);
+            const size_t e0 = (size_t)offs[k], e1 = (size_t)offs[k + 1];
+            if (drain_err == cudaSuccess) drain_err = dr.range(h.d_col + e0, sizeof(int) * (e1 - e0));
+            if (drain_err == cudaSuccess) drain_err = dr.range((const real *)h.d_val + e0, sizeof(real) * (e1 - e0));
+        }
+        dr.finish();
+    });
+    int rc = 0;
+    for (int k = 0; k < pieces; ++k) {
+        if (rows[k + 1] > rows[k])
+            rc = nsp::spgemm_numeric<real>(ctx, M, K, N, h.d_a_rpt, h.d_a_col, (const real *)h.d_a_val, b_rpt, b_col, b_val,
+                                           h.d_rpt64, h.d_col, (real *)h.d_val, rows[k], rows[k + 1] - rows[k]);
+        if (rc != 0 || cudaEventRecord(done[k], ctx->stream) != cudaSuccess) {
+            failed.store(1);
+            rc = rc ? rc : -1;
+            break;
+        }
+        launched.store(k + 1, std::memory_order_release);
+    }
+    drainer.join();
+    cudaStreamSynchronize(copy_st);
+    for (auto &e : done) cudaEventDestroy(e);
+    cudaEventDestroy(dr.ev[0]);
+    cudaEventDestroy(dr.ev[1]);
+    cudaStreamDestroy(copy_st);
+    if (rc != 0) return rc;
+    if (drain_err != cudaSuccess) return ctx->fail(NSP_ERR_CUDA, std::string("nsp_spgemm_host_stream: ") + cudaGetErrorString(drain_err));
+    if (h_nnz_c) *h_nnz_c = nnz;
+    if (h_checksum) *h_checksum = dr.sum;
+    if (h_bytes) *h_bytes = dr.total;
     return 0;
 }
 
@@ -445,6 +626,26 @@ int nsp_spgemm_host_d(nsp_context *ctx, int M, int K, int N, const int *h_a_rpt,
 {
     NSP_REQUIRE_CTX(ctx);
     return spgemm_host<double>(ctx, M, K, N, h_a_rpt, h_a_col, h_a_val, h_b_rpt, h_b_col, h_b_val, h_nnz_c);
+}
+
+int nsp_spgemm_host_stream_s(nsp_context *ctx, int M, int K, int N, const int *h_a_rpt, const int *h_a_col,
+                             const float *h_a_val, const int *h_b_rpt, const int *h_b_col, const float *h_b_val,
+                             void *h_stage, size_t stage_bytes, int pieces, long long *h_nnz_c,
+                             unsigned long long *h_checksum, long long *h_bytes)
+{
+    NSP_REQUIRE_CTX(ctx);
+    return spgemm_host_stream<float>(ctx, M, K, N, h_a_rpt, h_a_col, h_a_val, h_b_rpt, h_b_col, h_b_val, h_stage,
+                                     stage_bytes, pieces, h_nnz_c, h_checksum, h_bytes);
+}
+
+int nsp_spgemm_host_stream_d(nsp_context *ctx, int M, int K, int N, const int *h_a_rpt, const int *h_a_col,
+                             const double *h_a_val, const int *h_b_rpt, const int *h_b_col, const double *h_b_val,
+                             void *h_stage, size_t stage_bytes, int pieces, long long *h_nnz_c,
+                             unsigned long long *h_checksum, long long *h_bytes)
+{
+    NSP_REQUIRE_CTX(ctx);
+    return spgemm_host_stream<double>(ctx, M, K, N, h_a_rpt, h_a_col, h_a_val, h_b_rpt, h_b_col, h_b_val, h_stage,
+                                      stage_bytes, pieces, h_nnz_c, h_checksum, h_bytes);
 }
 
 static int host_fetch(nsp_context *ctx, int val_bytes, long long *h_c_rpt64, int *h_c_col, void *h_c_val)
@@ -480,47 +681,23 @@ int nsp_spgemm_host_drain(nsp_context *ctx, void *h_stage, size_t stage_bytes, u
     NSP_REQUIRE_CTX(ctx);
     nsp_host_result &h = ctx->host;
     if (!h.d_rpt64 || !h_stage || stage_bytes < 4096) return ctx->fail(NSP_ERR_ARG, "nsp_spgemm_host_drain: bad argument");
-    const size_t half = (stage_bytes / 2) & ~size_t(255);
-    cudaStream_t st = ctx->stream;
-    cudaEvent_t ev[2];
-    NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-    NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
-    unsigned long long sum = 0;
-    long long total = 0;
+    StagedDrain dr;
+    dr.stage = (unsigned char *)h_stage;
+    dr.half = (stage_bytes / 2) & ~size_t(255);
+    dr.st = ctx->stream;
+    NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&dr.ev[0], cudaEventDisableTiming));
+    NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&dr.ev[1], cudaEventDisableTiming));
     const void *src[3] = {h.d_rpt64, h.d_col, h.d_val};
     const size_t len[3] = {sizeof(long long) * ((size_t)h.M + 1), sizeof(int) * (size_t)h.nnz,
                            (size_t)h.val_bytes * (size_t)h.nnz};
-    int slot = 0;
-    bool pending[2] = {false, false};
-    size_t pend_len[2] = {0, 0};
-    auto consume = [&](int s) {
-        // fold the first and last word of the chunk: proves the bytes arrived without a host pass
-        // over tens of GB
-        cudaEventSynchronize(ev[s]);
-        const unsigned char *p = (const unsigned char *)h_stage + (size_t)s * half;
-        unsigned long long a = 0, b = 0;
-        memcpy(&a, p, pend_len[s] >= 8 ? 8 : pend_len[s]);
-        if (pend_len[s] >= 8) memcpy(&b, p + pend_len[s] - 8, 8);
-        sum = sum * 1099511628211ull + (a ^ (b << 1));
-        pending[s] = false;
-    };
-    for (int a = 0; a < 3; ++a) {
-        for (size_t off = 0; off < len[a]; off += half) {
-            const size_t n = len[a] - off < half ? len[a] - off : half;
-            if (pending[slot]) consume(slot);
-            NSP_CUDA_TRY(ctx, cudaMemcpyAsync((unsigned char *)h_stage + (size_t)slot * half,
-                                              (const unsigned char *)src[a] + off, n, cudaMemcpyDeviceToHost, st));
-            NSP_CUDA_TRY(ctx, cudaEventRecord(ev[slot], st));
-            pending[slot] = true;
-            pend_len[slot] = n;
-            total += (long long)n;
-            slot ^= 1;
-        }
-    }
-    if (pending[slot]) consume(slot);
-    if (pending[slot ^ 1]) consume(slot ^ 1);
-    cudaEventDestroy(ev[0]);
-    cudaEventDestroy(ev[1]);
+    cudaError_t e = cudaSuccess;
+    for (int a = 0; a < 3 && e == cudaSuccess; ++a) e = dr.range(src[a], len[a]);
+    dr.finish();
+    cudaEventDestroy(dr.ev[0]);
+    cudaEventDestroy(dr.ev[1]);
+    NSP_CUDA_TRY(ctx, e);
+    const unsigned long long sum = dr.sum;
+    const long long total = dr.total;
     if (h_checksum) *h_checksum = sum;
     if (h_bytes) *h_bytes = total;
     return 0;

@@ -312,3 +312,42 @@ def test_host_buffer_entry_point(ns, ctx):
     ok, msg = oracle.check_spgemm_answer((rpt, col, val), want)
     assert ok, msg
     ctx.check(ctx.lib.nsp_spgemm_host_release(ctx.handle))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_host_stream_entry_point(ns, ctx, dtype):
+    """nsp_spgemm_host_stream_*: host CSR in, C streamed to the host while it is computed (row ranges + a
+    drain thread).  The fold of the drained chunks must equal the fold of the oracle's C cut the same way."""
+    import ctypes as C
+
+    import torch
+
+    a = _rand(ns, 900, 700, 0.03, 41, dtype)
+    b = _rand(ns, 700, 1100, 0.03, 42, dtype)
+    want = _oracle(a, b)
+    w_rpt, w_col, w_val = want[0].astype(np.int64), want[1].astype(np.int32), want[2].astype(dtype)
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    stage = torch.empty(8192, dtype=torch.uint8).pin_memory()
+    half, pieces = 4096, 3
+    nnz, nbytes, csum = C.c_longlong(), C.c_longlong(), C.c_ulonglong()
+    fn = ctx.lib.nsp_spgemm_host_stream_d if dtype == np.float64 else ctx.lib.nsp_spgemm_host_stream_s
+    ctx.check(fn(ctx.handle, a.M, a.N, b.N, p(a.rpt), p(a.col), p(a.val), p(b.rpt), p(b.col), p(b.val),
+                 C.c_void_p(stage.data_ptr()), stage.numel(), pieces, C.byref(nnz), C.byref(csum), C.byref(nbytes)))
+    assert nnz.value == int(w_rpt[-1])
+    total = int(w_rpt[-1])
+    rows = [int(np.searchsorted(w_rpt, total // pieces * k, side="left")) for k in range(pieces)] + [a.M]
+    ranges = [w_rpt.tobytes()]
+    for k in range(pieces):
+        e0, e1 = int(w_rpt[rows[k]]), int(w_rpt[rows[k + 1]])
+        ranges += [w_col[e0:e1].tobytes(), w_val[e0:e1].tobytes()]
+    fold, moved = 0, 0
+    for r in ranges:
+        for off in range(0, len(r), half):
+            chunk = r[off:off + half]
+            x = int.from_bytes(chunk[:8].ljust(8, b"\0"), "little")
+            y = int.from_bytes(chunk[-8:], "little") if len(chunk) >= 8 else 0
+            fold = (fold * 1099511628211 + (x ^ ((y << 1) & 0xFFFFFFFFFFFFFFFF))) & 0xFFFFFFFFFFFFFFFF
+            moved += len(chunk)
+    assert nbytes.value == moved
+    assert csum.value == fold
+    ctx.check(ctx.lib.nsp_spgemm_host_release(ctx.handle))
