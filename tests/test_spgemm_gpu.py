@@ -351,3 +351,32 @@ def test_host_stream_entry_point(ns, ctx, dtype):
     assert nbytes.value == moved
     assert csum.value == fold
     ctx.check(ctx.lib.nsp_spgemm_host_release(ctx.handle))
+
+
+def test_host_drain_fold(ns, ctx):
+    """nsp_spgemm_host_s + nsp_spgemm_host_drain (the e2e leg of bench.py): the fold of the staged chunks of
+    rpt, col, val must equal the fold of the oracle's arrays."""
+    import ctypes as C
+
+    import torch
+
+    a = _rand(ns, 600, 500, 0.04, 51, np.float32)
+    b = _rand(ns, 500, 800, 0.04, 52, np.float32)
+    want = _oracle(a, b)
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    nnz, nbytes, csum = C.c_longlong(), C.c_longlong(), C.c_ulonglong()
+    ctx.check(ctx.lib.nsp_spgemm_host_s(ctx.handle, a.M, a.N, b.N, p(a.rpt), p(a.col), p(a.val), p(b.rpt), p(b.col),
+                                        p(b.val), C.byref(nnz)))
+    stage = torch.empty(8192, dtype=torch.uint8).pin_memory()
+    ctx.check(ctx.lib.nsp_spgemm_host_drain(ctx.handle, C.c_void_p(stage.data_ptr()), stage.numel(), C.byref(csum),
+                                            C.byref(nbytes)))
+    fold, moved = 0, 0
+    for r in (want[0].astype(np.int64).tobytes(), want[1].astype(np.int32).tobytes(), want[2].astype(np.float32).tobytes()):
+        for off in range(0, len(r), 4096):
+            chunk = r[off:off + 4096]
+            x = int.from_bytes(chunk[:8].ljust(8, b"\0"), "little")
+            y = int.from_bytes(chunk[-8:], "little") if len(chunk) >= 8 else 0
+            fold = (fold * 1099511628211 + (x ^ ((y << 1) & 0xFFFFFFFFFFFFFFFF))) & 0xFFFFFFFFFFFFFFFF
+            moved += len(chunk)
+    assert nnz.value == int(want[0][-1]) and nbytes.value == moved and csum.value == fold
+    ctx.check(ctx.lib.nsp_spgemm_host_release(ctx.handle))
