@@ -107,6 +107,16 @@ def test_unparsable_value_reads_as_zero_like_atof(tmp_path):
     assert same(got, oracle.read_mtx(str(f), np.float64)) and got["val"].tolist() == [0.0, 1.0, 100.0]
 
 
+def test_tabs_crlf_blank_lines_and_entry_limit(tmp_path):
+    """White space variants the reference's strchr(' ') tokenizer never sees are read the natural way; lines
+    beyond the nz of the size line are ignored like the reference's fixed-size COO arrays would require."""
+    f = tmp_path / "ws.mtx"
+    f.write_bytes(b"%%MatrixMarket matrix coordinate real general\r\n% c\r\n3 3 3\r\n1\t2\t2.5\r\n\r\n  3 1 -1\r\n2 2 7\r\n1 1 99\r\n")
+    got = read(f)
+    assert (got["M"], got["N"], got["nnz"]) == (3, 3, 3)
+    assert got["rpt"].tolist() == [0, 1, 2, 3] and got["col"].tolist() == [1, 1, 0] and got["val"].tolist() == [2.5, 7.0, -1.0]
+
+
 def test_reader_errors(tmp_path):
     with pytest.raises(IOError):
         read(tmp_path / "missing.mtx")

@@ -93,3 +93,26 @@ def test_partition_balances_intermediate_products():
     assert cuts[0] == 0 and cuts[-1] == 2 and total == 2
     cuts, total = mg.partition_rows_by_ip(np.zeros(4, np.int64), np.zeros(0, np.int64), np.zeros(4, np.int64), 2)
     assert cuts == [0, 0, 3] and total == 0
+
+
+def test_partition_rows_by_cost_balances_products_plus_output():
+    """partition_rows_by_cost: blocks of ~equal  products + w * nnz(C_i); w = 0 is the equal-product cut."""
+    import numpy as np
+
+    from nsparse_b200 import gen, partition_rows_by_cost, partition_rows_by_ip
+    from oracle import oracle
+
+    a = gen.rmat_csr(11, 8, seed=2, dtype=np.float64, native=False, values="ones")
+    c_rpt = oracle.spgemm(a.rpt, a.col, a.val, a.rpt, a.col, a.val, acc_double=True)[0].astype(np.int64)
+    cuts0, ip0 = partition_rows_by_ip(a.rpt, a.col, a.rpt, 4)
+    cuts1, ip1 = partition_rows_by_cost(a.rpt, a.col, a.rpt, c_rpt, 4, 0.0)
+    assert cuts1 == cuts0 and ip1 == ip0
+    w = 5.0
+    cuts, _ = partition_rows_by_cost(a.rpt, a.col, a.rpt, c_rpt, 4, w)
+    assert cuts[0] == 0 and cuts[-1] == a.M and all(x <= y for x, y in zip(cuts, cuts[1:]))
+    blen = np.diff(a.rpt).astype(np.int64)
+    ip_row = np.add.reduceat(np.concatenate([blen[a.col], [0]]), np.minimum(a.rpt[:-1], len(a.col)))
+    ip_row[np.diff(a.rpt) == 0] = 0
+    cost = ip_row + w * np.diff(c_rpt)
+    per = [cost[cuts[i]:cuts[i + 1]].sum() for i in range(4)]
+    assert max(per) - min(per) <= 2 * cost.max() + 1e-9     # within one (heaviest) row of each other
