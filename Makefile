@@ -12,13 +12,13 @@ OBJ       := build/obj
 LIBDIR    := nsparse_b200/lib
 BIN       := bin
 
-CORE_CU   := context spgemm_plan spgemm_symbolic spgemm_numeric_s spgemm_numeric_d c_api amb_convert amb_spmv amb_api
+CORE_CU   := context peer_push spgemm_plan spgemm_symbolic spgemm_numeric_s spgemm_numeric_d c_api amb_convert amb_spmv amb_api
 CORE_OBJ  := $(addprefix $(OBJ)/,$(addsuffix .o,$(CORE_CU))) $(OBJ)/gen.o $(OBJ)/mtx_reader.o
 
 .PHONY: all lib compat drivers clean oracle
 all: lib compat oracle
 
-lib: $(LIBDIR)/libnsparse_b200.so
+lib: $(LIBDIR)/libnsparse_b200.so $(LIBDIR)/libnsparse_gen.so
 
 $(OBJ)/%.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h $(SRC)/*.cuh include/*.h)
 	@mkdir -p $(OBJ)
@@ -35,6 +35,12 @@ $(OBJ)/mtx_reader.o: $(SRC)/mtx_reader.cpp include/nsparse_b200.h
 $(LIBDIR)/libnsparse_b200.so: $(CORE_OBJ)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -Xcompiler -fopenmp -lcudart -lgomp
+
+# the synthetic-input generator on its own (plain C++, no CUDA): bench.py's reference arm and the tests generate
+# their inputs without loading the product library
+$(LIBDIR)/libnsparse_gen.so: $(OBJ)/gen.o
+	@mkdir -p $(LIBDIR)
+	$(CXX) -shared -fopenmp -o $@ $^
 
 # ---- the nsparse.h API, one archive per precision (reference: .s.o / .d.o objects) ----
 compat: $(LIBDIR)/libnsparse_s.a $(LIBDIR)/libnsparse_d.a
@@ -71,6 +77,11 @@ drivers: compat
 	  $(NVCC) $(DRV_FLAGS) -DDOUBLE $(REF_DIR)/cuda-c/src/sample/spmv/spmv_amb.cu -o $(BIN)/amb_d -L$(LIBDIR) -lnsparse_d -lcusparse -lgomp; \
 	  echo "drivers built from $(REF_DIR) (sources unchanged)"; \
 	else echo "reference tree not present: drivers skipped"; fi
+	@# the same protocol driver that oracle/Makefile builds against the REFERENCE's SpGEMM, linked against this
+	@# library instead (test infrastructure: raw CSR in, reference timing protocol, C out)
+	@mkdir -p oracle/_ref
+	$(NVCC) $(DRV_FLAGS) -DNSP_OURS -DFLOAT  oracle/ref_gpu/dump_spgemm.cu -o oracle/_ref/dump_spgemm_ours_s -L$(LIBDIR) -lnsparse_s -lcusparse -lgomp
+	$(NVCC) $(DRV_FLAGS) -DNSP_OURS -DDOUBLE oracle/ref_gpu/dump_spgemm.cu -o oracle/_ref/dump_spgemm_ours_d -L$(LIBDIR) -lnsparse_d -lcusparse -lgomp
 
 oracle:
 	$(MAKE) -C oracle

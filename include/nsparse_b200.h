@@ -108,6 +108,15 @@ int nsp_spgemm_numeric_rows_d(nsp_context *ctx, int M, int K, int N, int row0, i
  * nnz > INT_MAX (the reference silently wraps, kernel_spgemm_hash_d.cu:1183). */
 int nsp_rpt64_to_rpt32(nsp_context *ctx, int M, const long long *d_rpt64, long long nnz, int *d_rpt32);
 
+/* Fold of a device CSR with an int64 row pointer, for parity checks at sizes nobody wants on the host (C = A^2
+ * of R-MAT scale 20 is 78 GB): h_hash2 = {position-dependent 64-bit hash of rpt[0..M], of col[0..nnz)} (exact,
+ * independent of the order the kernel visits the entries in), h_sum2 = {sum of val, sum of val * (col % 1021 + 1)}
+ * accumulated in double (floating-point atomics: equal up to rounding between runs).  Synchronises. */
+int nsp_csr_fold_s(nsp_context *ctx, int M, long long nnz, const long long *d_rpt64, const int *d_col,
+                   const float *d_val, unsigned long long *h_hash2, double *h_sum2);
+int nsp_csr_fold_d(nsp_context *ctx, int M, long long nnz, const long long *d_rpt64, const int *d_col,
+                   const double *d_val, unsigned long long *h_hash2, double *h_sum2);
+
 /* spgemm_kernel_hash (kernel_spgemm_hash_d.cu:1035-1075) with HOST buffers: copies A and
  * B to the device, runs both phases and leaves C on the device inside the context.
  * nsp_spgemm_host_fetch_* then copies C into caller-provided host arrays (any of the
@@ -162,14 +171,18 @@ int nsp_peer_free(nsp_context *ctx, void *d_ptr);
  * a destination opened by nsp_peer_open this is a copy-engine transfer over NVLink that needs no SM. */
 int nsp_copy_async(nsp_context *ctx, void *d_dst, const void *d_src, size_t bytes, void *cuda_stream);
 
-/* Fused numeric phase + allgatherv: after this call nsp_spgemm_numeric_* stores every entry of C it
- * produces not only at d_c_col / d_c_val but also at d_peer_col[p] / d_peer_val[p] + elem_offset + (the
- * same index) for p < npeers (at most 7): the bases of the FULL C.col / C.val arrays of the other GPUs and
- * the displacement of this rank's row block in them.  The heavy rows are stored by the kernel that
- * computes them, chunk by chunk, with the same coalesced stores as the local copy; a follow-up kernel
- * pushes the remaining rows.  npeers == 0 switches it off. */
+/* Numeric phase overlapped with the allgatherv of C: after this call nsp_spgemm_numeric_* also sends every
+ * entry of C it produces to d_peer_col[p] / d_peer_val[p] + elem_offset + (the same index) for p < npeers (at
+ * most 7): the bases of the FULL C.col / C.val arrays of the other GPUs and the displacement of this rank's
+ * row block in them (d_c_col / d_c_val passed to the numeric call must then be this rank's own full arrays
+ * + elem_offset).  The block is cut into tiles of 8192 entries; the numeric kernels count finished entries
+ * per tile, and a persistent pusher kernel on a few SMs of its own (option "push_sms", default 16) stores
+ * every completed tile into all peers through the TMA (cp.async.bulk shared -> peer global) while the other
+ * SMs keep computing.  The transfer is complete when the context's stream is.  npeers == 0 switches it off.
+ * nsp_spgemm_peers_status synchronises and reports whether the pusher ever gave up waiting (it never should). */
 int nsp_spgemm_set_peers(nsp_context *ctx, int npeers, void *const *d_peer_col, void *const *d_peer_val,
                          long long elem_offset);
+int nsp_spgemm_peers_status(nsp_context *ctx, int *h_error);
 int nsp_push_to_peers(nsp_context *ctx, int npeers, void *const *d_peer_bases, size_t byte_offset,
                       const void *d_src, size_t nbytes);
 

@@ -50,6 +50,8 @@ SIGNATURES = {
     "nsp_spgemm_numeric_rows_s": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [vp] * 9),
     "nsp_spgemm_numeric_rows_d": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [vp] * 9),
     "nsp_rpt64_to_rpt32": (C.c_int, [vp, C.c_int, vp, ll, vp]),
+    "nsp_csr_fold_s": (C.c_int, [vp, C.c_int, ll, vp, vp, vp, C.POINTER(C.c_ulonglong * 2), C.POINTER(C.c_double * 2)]),
+    "nsp_csr_fold_d": (C.c_int, [vp, C.c_int, ll, vp, vp, vp, C.POINTER(C.c_ulonglong * 2), C.POINTER(C.c_double * 2)]),
     "nsp_spgemm_host_s": (C.c_int, [vp, C.c_int, C.c_int, C.c_int] + [vp] * 6 + [C.POINTER(ll)]),
     "nsp_spgemm_host_d": (C.c_int, [vp, C.c_int, C.c_int, C.c_int] + [vp] * 6 + [C.POINTER(ll)]),
     "nsp_spgemm_host_fetch_s": (C.c_int, [vp, vp, vp, vp]),
@@ -76,6 +78,7 @@ SIGNATURES = {
     "nsp_peer_free": (C.c_int, [vp, vp]),
     "nsp_copy_async": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
     "nsp_spgemm_set_peers": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), ll]),
+    "nsp_spgemm_peers_status": (C.c_int, [vp, C.POINTER(C.c_int)]),
     "nsp_push_multicast": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t]),
     "nsp_push_to_peers": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.c_size_t, vp, C.c_size_t]),
     "nsp_read_mtx": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(ll),

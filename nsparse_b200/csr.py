@@ -58,6 +58,20 @@ class DeviceCSR64:
         self.M, self.N, self.nnz, self.intprod = M, N, int(nnz), int(intprod)
         self.d_rpt64, self.d_col, self.d_val = d_rpt64, d_col, d_val
 
+    def fold(self, ctx):
+        """(hash of rpt, hash of col, sum of val, column-weighted sum of val) computed on the device
+        (nsp_csr_fold_*): the hashes are exact, the sums equal up to fp64 rounding between runs."""
+        import ctypes as C
+
+        import torch
+
+        h, f = (C.c_ulonglong * 2)(), (C.c_double * 2)()
+        fn = ctx.lib.nsp_csr_fold_d if self.d_val.dtype == torch.float64 else ctx.lib.nsp_csr_fold_s
+        ctx.use_torch_stream()
+        ctx.check(fn(ctx.handle, self.M, self.nnz, C.c_void_p(self.d_rpt64.data_ptr()), C.c_void_p(self.d_col.data_ptr()),
+                     C.c_void_p(self.d_val.data_ptr()), C.byref(h), C.byref(f)))
+        return int(h[0]), int(h[1]), float(f[0]), float(f[1])
+
     # csr_memcpyDtH (nsparse.cu:158-168)
     def to_host(self):
         return (self.d_rpt64.cpu().numpy(), self.d_col[: self.nnz].cpu().numpy(),

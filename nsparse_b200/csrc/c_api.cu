@@ -16,6 +16,68 @@ using nsp::context_destroy;
     if (!(ctx)) return NSP_ERR_ARG; \
     cudaSetDevice((ctx)->device)
 
+// ---- fold of a device CSR (parity checks at sizes no host copy is wanted for) ---------------------------
+__device__ __forceinline__ unsigned long long fold_mix(unsigned long long x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256)
+fold_csr_kernel(const long long *__restrict__ rpt, const int *__restrict__ col, const real *__restrict__ val, int M,
+                long long nnz, unsigned long long *__restrict__ out_h, double *__restrict__ out_f)
+{
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    unsigned long long hr = 0, hc = 0;
+    double sv = 0.0, sw = 0.0;
+    for (long long i = tid; i <= M; i += nth) hr += fold_mix((unsigned long long)i * 0x100000001B3ull ^ (unsigned long long)rpt[i]);
+    for (long long i = tid; i < nnz; i += nth) {
+        const int c = col[i];
+        hc += fold_mix((unsigned long long)i * 0x100000001B3ull ^ (unsigned long long)(unsigned)c);
+        const double v = (double)val[i];
+        sv += v;
+        sw += v * (double)((c % 1021) + 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        hr += __shfl_xor_sync(0xffffffffu, hr, o);
+        hc += __shfl_xor_sync(0xffffffffu, hc, o);
+        sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        sw += __shfl_xor_sync(0xffffffffu, sw, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out_h, hr);
+        atomicAdd(out_h + 1, hc);
+        atomicAdd(out_f, sv);
+        atomicAdd(out_f + 1, sw);
+    }
+}
+
+template <typename real>
+static int fold_csr(nsp_context *ctx, int M, long long nnz, const long long *d_rpt64, const int *d_col, const real *d_val,
+                    unsigned long long *h_hash2, double *h_sum2)
+{
+    if (M < 0 || nnz < 0 || !d_rpt64 || !h_hash2 || !h_sum2) return ctx->fail(NSP_ERR_ARG, "nsp_csr_fold: bad argument");
+    unsigned long long *d = nullptr;
+    NSP_CUDA_TRY(ctx, cudaMalloc((void **)&d, 32));
+    NSP_CUDA_TRY(ctx, cudaMemsetAsync(d, 0, 32, ctx->stream));
+    fold_csr_kernel<real><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_rpt64, d_col, d_val, M, nnz, d, reinterpret_cast<double *>(d + 2));
+    ctx->launches += 1;
+    unsigned long long h[4];
+    cudaError_t e = cudaMemcpyAsync(h, d, 32, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    NSP_CUDA_TRY(ctx, e);
+    h_hash2[0] = h[0];
+    h_hash2[1] = h[1];
+    memcpy(h_sum2, h + 2, 16);
+    return 0;
+}
+
 extern "C" {
 
 int nsp_create(nsp_context **ctx, int device) { return context_create(ctx, device); }
@@ -25,6 +87,7 @@ const char *nsp_last_error(nsp_context *ctx) { return ctx ? ctx->err.c_str() : "
 int nsp_set_stream(nsp_context *ctx, void *cuda_stream)
 {
     NSP_REQUIRE_CTX(ctx);
+    if (ctx->stream == (cudaStream_t)cuda_stream) return 0;      // bindings call this before every op: no sync then
     NSP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stream = (cudaStream_t)cuda_stream;
     return 0;
@@ -47,6 +110,7 @@ int nsp_set_option(nsp_context *ctx, const char *name, long long value)
     else if (!strcmp(name, "no_vec")) ctx->opt_no_vec = value;
     else if (!strcmp(name, "no_fork")) ctx->opt_no_fork = value;
     else if (!strcmp(name, "num_cap")) ctx->opt_num_cap = value;
+    else if (!strcmp(name, "push_sms")) ctx->opt_push_sms = value;
     else if (!strcmp(name, "phase_timing")) {
         // value 1: start accumulating; value 2: print the totals (cycles summed over CTAs) and reset
         if (value == 2 && ctx->d_phase) {
@@ -172,6 +236,24 @@ int nsp_spgemm_set_peers(nsp_context *ctx, int npeers, void *const *d_peer_col, 
     return 0;
 }
 
+int nsp_spgemm_peers_status(nsp_context *ctx, int *h_error)
+{
+    NSP_REQUIRE_CTX(ctx);
+    if (!h_error) return ctx->fail(NSP_ERR_ARG, "nsp_spgemm_peers_status: bad argument");
+    *h_error = 0;
+    if (!ctx->d_push_ws) return 0;
+    NSP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    int ctl[3] = {0, 0, 0};
+    NSP_CUDA_TRY(ctx, cudaMemcpy(ctl, ctx->d_push_ws, sizeof(ctl), cudaMemcpyDeviceToHost));
+    if (ctl[2]) {
+        *h_error = 1;
+        NSP_CUDA_TRY(ctx, cudaMemset(ctx->d_push_ws + 2, 0, sizeof(int)));
+        return ctx->fail(NSP_ERR_CUDA, "multi-GPU allgatherv: the pusher kernel gave up waiting for a tile of C (" +
+                                           std::to_string(ctl[0]) + " tiles were published)");
+    }
+    return 0;
+}
+
 // The same through an NVSwitch multicast address: ONE multimem.st per 16 bytes, the switch replicates the
 // write into the buffer of every GPU bound to the multicast object (NVLS).
 __global__ void __launch_bounds__(256)
@@ -244,6 +326,20 @@ int nsp_push_to_peers(nsp_context *ctx, int npeers, void *const *d_peer_bases, s
     ctx->launches += 1;
     NSP_CUDA_TRY(ctx, cudaGetLastError());
     return 0;
+}
+
+int nsp_csr_fold_s(nsp_context *ctx, int M, long long nnz, const long long *d_rpt64, const int *d_col, const float *d_val,
+                   unsigned long long *h_hash2, double *h_sum2)
+{
+    NSP_REQUIRE_CTX(ctx);
+    return fold_csr<float>(ctx, M, nnz, d_rpt64, d_col, d_val, h_hash2, h_sum2);
+}
+
+int nsp_csr_fold_d(nsp_context *ctx, int M, long long nnz, const long long *d_rpt64, const int *d_col, const double *d_val,
+                   unsigned long long *h_hash2, double *h_sum2)
+{
+    NSP_REQUIRE_CTX(ctx);
+    return fold_csr<double>(ctx, M, nnz, d_rpt64, d_col, d_val, h_hash2, h_sum2);
 }
 
 long long nsp_launch_count(nsp_context *ctx) { return ctx ? ctx->launches : 0; }
@@ -538,32 +634,48 @@ static int spgemm_host_stream(nsp_context *ctx, int M, int K, int N, const int *
         return -1;
     nsp_host_result &h = ctx->host;
     if (M < pieces) pieces = M > 0 ? M : 1;
-    // row cuts of equal output
+    // row cuts of equal output (the 65-entry scratch lives in the context's host-call state)
     int rows[65];
     long long offs[65];
     {
-        int *d_rows = nullptr;
-        long long *d_offs = nullptr;
-        NSP_CUDA_TRY(ctx, cudaMalloc((void **)&d_rows, sizeof(int) * 65));
-        NSP_CUDA_TRY(ctx, cudaMalloc((void **)&d_offs, sizeof(long long) * 65));
-        find_row_cuts_kernel<<<1, 128, 0, ctx->stream>>>(h.d_rpt64, M, nnz, pieces, d_rows, d_offs);
+        if (!h.d_cut_rows) {
+            NSP_CUDA_TRY(ctx, cudaMalloc((void **)&h.d_cut_rows, sizeof(int) * 65));
+            NSP_CUDA_TRY(ctx, cudaMalloc((void **)&h.d_cut_offs, sizeof(long long) * 65));
+        }
+        find_row_cuts_kernel<<<1, 128, 0, ctx->stream>>>(h.d_rpt64, M, nnz, pieces, h.d_cut_rows, h.d_cut_offs);
         ctx->launches += 1;
-        NSP_CUDA_TRY(ctx, cudaMemcpyAsync(rows, d_rows, sizeof(int) * (pieces + 1), cudaMemcpyDeviceToHost, ctx->stream));
-        NSP_CUDA_TRY(ctx, cudaMemcpyAsync(offs, d_offs, sizeof(long long) * (pieces + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        NSP_CUDA_TRY(ctx, cudaMemcpyAsync(rows, h.d_cut_rows, sizeof(int) * (pieces + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        NSP_CUDA_TRY(ctx, cudaMemcpyAsync(offs, h.d_cut_offs, sizeof(long long) * (pieces + 1), cudaMemcpyDeviceToHost, ctx->stream));
         NSP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(d_rows);
-        cudaFree(d_offs);
     }
-    cudaStream_t copy_st = nullptr;
-    NSP_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
-    std::vector<cudaEvent_t> done((size_t)pieces);
-    for (auto &e : done) NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // stream + events of the drain, released on every exit path
+    struct DrainRes {
+        cudaStream_t st = nullptr;
+        std::vector<cudaEvent_t> done;
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        ~DrainRes()
+        {
+            if (st) cudaStreamSynchronize(st);
+            for (auto e : done)
+                if (e) cudaEventDestroy(e);
+            for (auto e : ev)
+                if (e) cudaEventDestroy(e);
+            if (st) cudaStreamDestroy(st);
+        }
+    } res;
+    NSP_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&res.st, cudaStreamNonBlocking));
+    res.done.assign((size_t)pieces, nullptr);
+    for (auto &e : res.done) NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&res.ev[0], cudaEventDisableTiming));
+    NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&res.ev[1], cudaEventDisableTiming));
+    cudaStream_t copy_st = res.st;
+    std::vector<cudaEvent_t> &done = res.done;
     StagedDrain dr;
     dr.stage = (unsigned char *)h_stage;
     dr.half = (stage_bytes / 2) & ~size_t(255);
     dr.st = copy_st;
-    NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&dr.ev[0], cudaEventDisableTiming));
-    NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&dr.ev[1], cudaEventDisableTiming));
+    dr.ev[0] = res.ev[0];
+    dr.ev[1] = res.ev[1];
     std::atomic<int> launched(0);
     std::atomic<int> failed(0);
     cudaError_t drain_err = cudaSuccess;
@@ -598,10 +710,6 @@ static int spgemm_host_stream(nsp_context *ctx, int M, int K, int N, const int *
     }
     drainer.join();
     cudaStreamSynchronize(copy_st);
-    for (auto &e : done) cudaEventDestroy(e);
-    cudaEventDestroy(dr.ev[0]);
-    cudaEventDestroy(dr.ev[1]);
-    cudaStreamDestroy(copy_st);
     if (rc != 0) return rc;
     if (drain_err != cudaSuccess) return ctx->fail(NSP_ERR_CUDA, std::string("nsp_spgemm_host_stream: ") + cudaGetErrorString(drain_err));
     if (h_nnz_c) *h_nnz_c = nnz;
@@ -711,6 +819,7 @@ int nsp_spgemm_host_release(nsp_context *ctx)
     cudaFree(h.d_rpt64); cudaFree(h.d_col); cudaFree(h.d_val);
     cudaFree(h.d_a_rpt); cudaFree(h.d_a_col); cudaFree(h.d_a_val);
     cudaFree(h.d_b_rpt); cudaFree(h.d_b_col); cudaFree(h.d_b_val);
+    cudaFree(h.d_cut_rows); cudaFree(h.d_cut_offs);
     h = nsp_host_result();
     return 0;
 }

@@ -25,16 +25,60 @@ constexpr int kEmptyKey = -1;              // columns are >= 0, so -1 marks a fr
 // the SpGEMM does not depend on the hash.
 constexpr unsigned kHashMul = 0x9E3779B1u;
 
-// Peer copies of C for the fused compute + allgatherv of the multi-GPU SpGEMM: base pointers of the FULL
-// C.col / C.val arrays on the other GPUs (mapped with CUDA IPC) and the element displacement of this
-// rank's row block.  n == 0: single GPU.
+// Multi-GPU allgatherv of C, overlapped with the numeric phase (peer_push.cu).  Every GPU holds the FULL
+// C.col / C.val arrays; the bases of the other GPUs' copies are mapped into this process (CUDA IPC, or plain
+// peer access inside one process) and `off` is the element displacement of this rank's row block in them.
+// The block is cut into TILES of 2^kTileLog consecutive entries, aligned in the full arrays.  The numeric
+// kernels only COUNT: whoever has written entries [s, e) of the block adds the overlap to the counter of every
+// tile it touches (tiles_done below), and the thread that completes a tile appends it to a ready queue.  A
+// persistent pusher kernel on a few SMs of its own (push_tiles_kernel) takes the ready tiles in completion
+// order and stores them into every peer through the TMA (cp.async.bulk shared -> peer global), so the NVLink
+// transfer runs next to the compute instead of inside the computing CTAs.  n == 0: single GPU.
 constexpr int kMaxPeerOut = 7;
+constexpr int kTileLog = 13;               // 8192 entries: 32 KiB of C.col + 32 / 64 KiB of C.val per tile
 struct PeerOut {
     int n = 0;
     long long off = 0;
     int *col[kMaxPeerOut] = {};
     void *val[kMaxPeerOut] = {};
+    long long tile0 = 0;        // index of the first tile of the block (off >> kTileLog)
+    int ntiles = 0;
+    long long nnz = 0;          // entries of the block
+    int *tile_cnt = nullptr;    // [ntiles] entries written so far
+    int *queue = nullptr;       // [ntiles] ready tiles (block relative), -1 = not yet published
+    int *q_ctl = nullptr;       // [0] tail (producers), [1] head (pusher tickets), [2] error flag
 };
+
+// entries the block [off, off + nnz) has in its tile t (block relative)
+__host__ __device__ __forceinline__ int tile_len(const PeerOut &p, int t)
+{
+    const long long lo = (p.tile0 + t) << kTileLog, hi = lo + (1ll << kTileLog);
+    const long long a = lo > p.off ? lo : p.off, b = hi < p.off + p.nnz ? hi : p.off + p.nnz;
+    return (int)(b - a);
+}
+
+#ifdef __CUDACC__
+// Called by ONE thread after the entries [first, first + count) of this rank's block (indices relative to the
+// block) have been written to the local C.col AND C.val by its group (CTA or warp) and a group barrier has
+// ordered those writes before this call; the fence makes them visible at GPU scope before the counters move.
+__device__ __forceinline__ void tiles_done(const PeerOut &p, long long first, long long count)
+{
+    if (count <= 0) return;
+    __threadfence();
+    const long long s = p.off + first, e = s + count;
+    for (long long t = s >> kTileLog; t <= (e - 1) >> kTileLog; ++t) {
+        const long long lo = t << kTileLog, hi = lo + (1ll << kTileLog);
+        const int add = (int)((e < hi ? e : hi) - (s > lo ? s : lo));
+        const int ti = (int)(t - p.tile0);
+        const int old = atomicAdd(p.tile_cnt + ti, add);
+        if (old + add == tile_len(p, ti)) {
+            __threadfence();                                  // the other writers' entries (seen through the counter)
+            const int slot = atomicAdd(p.q_ctl, 1);
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.queue + slot), "r"(ti) : "memory");
+        }
+    }
+}
+#endif
 
 struct Error {
     int code;

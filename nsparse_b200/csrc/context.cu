@@ -6,6 +6,8 @@ int nsp_context::arena_reserve(size_t total_bytes)
     if (total_bytes <= arena_bytes) return 0;
     // growing: nothing of ours may still be running on the old block
     cudaError_t e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess && aux_stream) e = cudaStreamSynchronize(aux_stream);
+    sp.join_pending = false;
     if (e != cudaSuccess) return fail(-1, std::string("arena sync: ") + cudaGetErrorString(e));
     if (arena) cudaFree(arena);
     arena = nullptr;
@@ -33,9 +35,16 @@ int context_create(nsp_context **out, int device)
     if (cudaSetDevice(device) != cudaSuccess) return -1;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
-    if (prop.major < 10) {
+    // the library holds sm_100a SASS only (arch-specific code is not forward compatible: sm_103 / sm_120 would
+    // pass a "major >= 10" test and then fail at the first launch with "no kernel image")
+    if (prop.major != 10 || prop.minor != 0) {
         fprintf(stderr, "nsparse_b200: device %d is sm_%d%d; this build targets sm_100a (B200) only\n", device,
                 prop.major, prop.minor);
+        return -1;
+    }
+    if ((int)prop.sharedMemPerBlockOptin < nsp::kMaxSmemOptin) {
+        fprintf(stderr, "nsparse_b200: device %d offers %zu bytes of opt-in shared memory per block, the kernels "
+                        "are laid out for %d\n", device, (size_t)prop.sharedMemPerBlockOptin, nsp::kMaxSmemOptin);
         return -1;
     }
     nsp_context *ctx = new nsp_context();
@@ -77,10 +86,23 @@ int context_destroy(nsp_context *ctx)
         cudaStreamSynchronize(ctx->aux_stream);
         cudaStreamDestroy(ctx->aux_stream);
     }
+    if (ctx->push_stream) {
+        cudaStreamSynchronize(ctx->push_stream);
+        cudaStreamDestroy(ctx->push_stream);
+        cudaEventDestroy(ctx->ev_push_fork);
+        cudaEventDestroy(ctx->ev_push_join);
+    }
+    cudaFree(ctx->d_push_ws);
     if (ctx->mem_pool) cudaMemPoolDestroy(ctx->mem_pool);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->d_phase) cudaFree(ctx->d_phase);
+    for (auto &r : ctx->prof) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    ctx->prof.clear();
     if (ctx->sp.h_scalars) cudaFreeHost(ctx->sp.h_scalars);
     if (ctx->sp.h_bins) cudaFreeHost(ctx->sp.h_bins);
     if (ctx->sp.h_binsum) cudaFreeHost(ctx->sp.h_binsum);
@@ -94,6 +116,8 @@ int context_destroy(nsp_context *ctx)
     cudaFree(h.d_b_rpt);
     cudaFree(h.d_b_col);
     cudaFree(h.d_b_val);
+    cudaFree(h.d_cut_rows);
+    cudaFree(h.d_cut_offs);
     delete ctx;
     return 0;
 }

@@ -42,6 +42,8 @@ struct nsp_host_result {
     size_t a_nnz_cap = 0, b_nnz_cap = 0;
     int a_m_cap = 0, b_m_cap = 0;
     int in_val_bytes = 0;
+    int *d_cut_rows = nullptr;        // row cuts of nsp_spgemm_host_stream_* (65 entries each)
+    long long *d_cut_offs = nullptr;
 };
 
 struct nsp_prof_rec {
@@ -89,6 +91,14 @@ struct nsp_context {
 
     nsp_spgemm_state sp;
     nsp::PeerOut peer_out;   // nsp_spgemm_set_peers
+    // tile hand-off + pusher kernel of the multi-GPU allgatherv (peer_push.cu)
+    cudaStream_t push_stream = nullptr;
+    cudaEvent_t ev_push_fork = nullptr, ev_push_join = nullptr;
+    int *d_push_ws = nullptr;            // [8 control ints][cap tile counters][cap queue slots]
+    size_t push_cap = 0;
+    bool push_active = false;
+    int push_ctas = 0;
+    long long opt_push_sms = 0;          // CTAs (= SMs) of the pusher kernel (0: default 16)
     nsp_host_result host;
 
     long long launches = 0;
@@ -157,5 +167,8 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
                    const real *a_val, const int *b_rpt, const int *b_col, const real *b_val,
                    const long long *c_rpt64, int *c_col, real *c_val, int row0 = 0, int nrows = -1);
 int rpt64_to_rpt32(nsp_context *ctx, int M, const long long *rpt64, long long nnz, int *rpt32);
+// peer_push.cu
+int peer_push_begin(nsp_context *ctx, const int *c_col_full, const void *c_val_full, int val_bytes, long long nnz_block);
+int peer_push_end(nsp_context *ctx);
 
 }  // namespace nsp

@@ -33,7 +33,7 @@ num_pwarp_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                  const real *__restrict__ a_val, const int *__restrict__ b_rpt,
                  const int *__restrict__ b_col, const real *__restrict__ b_val,
                  const long long *__restrict__ c_rpt, int *__restrict__ c_col, real *__restrict__ c_val,
-                 const int *__restrict__ row_perm, const int *__restrict__ bins)
+                 const int *__restrict__ row_perm, const int *__restrict__ bins, const __grid_constant__ PeerOut peer)
 {
     __shared__ int keys[(256 / kPwNum) * kPwNumSlots];
     __shared__ real vals[(256 / kPwNum) * kPwNumSlots];
@@ -77,6 +77,7 @@ num_pwarp_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
             }
         }
         __syncwarp();
+        if (peer.n > 0 && r < n && t == 0) tiles_done(peer, c_rpt[rid], c_rpt[rid + 1] - c_rpt[rid]);
     }
 }
 
@@ -88,7 +89,7 @@ num_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                 const int *__restrict__ b_col, const real *__restrict__ b_val,
                 const long long *__restrict__ c_rpt, int *__restrict__ c_col, real *__restrict__ c_val,
                 const int *__restrict__ row_perm, int *__restrict__ bins, int bin_lo, int bin_hi,
-                int queue, int tmax)
+                int queue, int tmax, const __grid_constant__ PeerOut peer)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NG = BS / GROUP;
@@ -133,6 +134,7 @@ num_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
             c_val[off + i] = vals[i];
         }
         group_sync<GROUP>();
+        if (peer.n > 0 && t == 0) tiles_done(peer, off, nnz);
     }
 }
 
@@ -377,30 +379,14 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                 PH(8);
                 real *cv = c_val + out + r0;
                 int *cc = c_col + out + r0;
-                if (!kPeers) {
-                    for (int i = t; i < cnt; i += BS) {
-                        const int j = acc_swz(i);
-                        cv[i] = acc[j];
-                        cc[i] = cols[j];
-                    }
-                } else {
-                    // fused allgatherv: the finished chunk goes to this GPU's C and, with the same coalesced
-                    // stores, to the C of every peer over NVLink (posted writes: nothing waits for them)
-                    const long long g = peer.off + out + r0;
-                    for (int i = t; i < cnt; i += BS) {
-                        const int j = acc_swz(i);
-                        const real v = acc[j];
-                        const int c = cols[j];
-                        cv[i] = v;
-                        cc[i] = c;
-#pragma unroll 1
-                        for (int p = 0; p < peer.n; ++p) {
-                            static_cast<real *>(peer.val[p])[g + i] = v;
-                            peer.col[p][g + i] = c;
-                        }
-                    }
+                for (int i = t; i < cnt; i += BS) {
+                    const int j = acc_swz(i);
+                    cv[i] = acc[j];
+                    cc[i] = cols[j];
                 }
                 __syncthreads();                       // the next chunk reuses the buffers
+                // multi-GPU: the chunk is final in the local C; count it into its tiles (peer_push.cu sends them)
+                if (kPeers && t == 0) tiles_done(peer, out + r0, cnt);
                 PH(9);
             }
             // Rows with more than BS entries of A (0.1 % of the rows, a seventh of the products on R-MAT)
@@ -433,17 +419,7 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                     }
                     __syncthreads();
                     int *cc = c_col + out + r0;
-                    if (!kPeers) {
-                        for (int i = t; i < cnt; i += BS) cc[i] = cols[i];
-                    } else {
-                        const long long g = peer.off + out + r0;
-                        for (int i = t; i < cnt; i += BS) {
-                            const int c = cols[i];
-                            cc[i] = c;
-#pragma unroll 1
-                            for (int p = 0; p < peer.n; ++p) peer.col[p][g + i] = c;
-                        }
-                    }
+                    for (int i = t; i < cnt; i += BS) cc[i] = cols[i];
                     __syncthreads();
                 }
                 PH(6);
@@ -468,16 +444,10 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                     PH(10);
                 }
                 if (kPeers) {
-                    // the row is complete once every thread's reds are performed: read it back from L2 and
-                    // hand it to the peers (fused allgatherv of the red.global rows)
+                    // the window's entries are final once every thread's reds are performed
                     __threadfence();
                     __syncthreads();
-                    const long long g = peer.off + out;
-                    for (int i = t; i < tile_nnz; i += BS) {
-                        const real v = __ldcg(cv + i);
-#pragma unroll 1
-                        for (int p = 0; p < peer.n; ++p) static_cast<real *>(peer.val[p])[g + i] = v;
-                    }
+                    if (t == 0) tiles_done(peer, out, tile_nnz);
                 }
             }
             out += tile_nnz;
@@ -490,39 +460,6 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
     }
 #endif
 #undef PH
-}
-
-// Rows of C that num_bitmap_kernel did not store into the peers itself (see PeerOut): everything below
-// the bitmap class.  A CTA takes eight consecutive rows: short rows one warp each, long rows all eight.
-template <typename real>
-__global__ void __launch_bounds__(256)
-push_rows_kernel(int M, const int *__restrict__ a_rpt, const long long *__restrict__ c_rpt,
-                 const int *__restrict__ c_col, const real *__restrict__ c_val, int bm_bin, int shift, bool fused_class,
-                 const __grid_constant__ PeerOut peer)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int base = blockIdx.x * 8; base < M; base += gridDim.x * 8) {
-        for (int r = 0; r < 8 && base + r < M; ++r) {
-            const int i = base + r;
-            const long long s = c_rpt[i], e = c_rpt[i + 1];
-            const long long n = e - s;
-            if (n == 0) continue;
-            const bool fused = fused_class && log_bin((int)(n < 0x7fffffffll ? n : 0x7fffffffll), shift) >= bm_bin;
-            if (fused) continue;
-            const bool whole_cta = n > 1024;
-            if (!whole_cta && wid != r) continue;
-            const long long first = s + (whole_cta ? threadIdx.x : lane);
-            const int stride = whole_cta ? 256 : 32;
-            for (long long k = first; k < e; k += stride) {
-                const int c = c_col[k];
-                const real v = c_val[k];
-                for (int p = 0; p < peer.n; ++p) {
-                    peer.col[p][peer.off + k] = c;
-                    static_cast<real *>(peer.val[p])[peer.off + k] = v;
-                }
-            }
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -570,7 +507,7 @@ static int launch_num_hash(nsp_context *ctx, const char *name, int grid, size_t 
     auto kern = num_hash_kernel<real, GROUP, BS>;
     NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     num_prof_class(ctx, name, bin_lo, bin_hi);
-    kern<<<grid, BS, smem, ctx->stream>>>(NSP_NUM_ARGS, bin_lo, bin_hi, queue, tmax);
+    kern<<<grid, BS, smem, ctx->stream>>>(NSP_NUM_ARGS, bin_lo, bin_hi, queue, tmax, ctx->peer_out);
     ctx->prof_end();
     ctx->launches += 1;
     NSP_CUDA_TRY(ctx, cudaGetLastError());
@@ -587,6 +524,8 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
         return ctx->fail(-2, "nsp_spgemm_numeric: call nsp_spgemm_symbolic on the same context and shapes first");
     if (nrows < 0) nrows = M - row0;
     if (row0 < 0 || nrows < 0 || row0 + nrows > M) return ctx->fail(-2, "nsp_spgemm_numeric: bad row range");
+    if (ctx->peer_out.n > 0 && (row0 != 0 || nrows != M))
+        return ctx->fail(-2, "nsp_spgemm_numeric_rows: not available while peers are set (nsp_spgemm_set_peers)");
     // Rows [row0, row0 + nrows) only (the multi-GPU pipeline computes a block in pieces so that finished
     // pieces travel to the peers while the next one is computed): every per-row array is entered at row0,
     // row ids are then relative to it, and the row pointers keep indexing the full col / val arrays.
@@ -627,12 +566,32 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
         if (bm_bin > 10) bm_bin = 10;
     }
     const int sms = ctx->sm_count;
-    if (num_rows_in(sp, bm_bin, kNumBins - 1) > 0) {
+    // the side-stream launch of the long rows is joined on EVERY exit path, also the early error returns of the
+    // launches below (the aux kernel reads d_bins / d_row_perm, which the next call rewrites)
+    struct JoinGuard {
+        nsp_context *ctx;
+        ~JoinGuard()
+        {
+            if (ctx->sp.join_pending) {
+                cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+                ctx->sp.join_pending = false;
+            }
+        }
+    } join_guard{ctx};
+    const bool peers = ctx->peer_out.n > 0;
+    long long nnz_block = 0;
+    for (int b = 0; b < kNumBins; ++b) nnz_block += (long long)sp.h_binsum[kSumCnt + b];
+    // multi-GPU: the pusher kernel takes its SMs first (peer_push.cu); the computing kernels only count tiles
+    if (peers && peer_push_begin(ctx, c_col - ctx->peer_out.off, c_val - ctx->peer_out.off, (int)sizeof(real), nnz_block) != 0)
+        return -1;
+    const int push_sms = ctx->push_active ? ctx->push_ctas : 0;
+
+    auto launch_bitmap = [&]() -> int {
+        if (num_rows_in(sp, bm_bin, kNumBins - 1) == 0) return 0;
         if (cap < 128 || ((1ll << wshift) + cap - 1) / cap > kMaxChunks)
             return ctx->fail(-4, "nsp_spgemm_numeric: shared memory too small for the bitmap kernel");
         const size_t smem = fixed + (size_t)cap * (sizeof(real) + sizeof(int));
-        const int grid = num_imin(num_rows_in(sp, bm_bin, kNumBins - 1), (long long)sms);
-        const bool peers = ctx->peer_out.n > 0;
+        const int grid = num_imin(num_rows_in(sp, bm_bin, kNumBins - 1), (long long)(sms - push_sms));
         // [multi][peers][sorted]
         void (*kerns[2][2][2])(const int *, const int *, const real *, const int *, const int *, const real *,
                                const long long *, int *, real *, const int *, int *, int, int, int, int, int, int, int,
@@ -668,53 +627,58 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
         }
         if (forked) NSP_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
         sp.join_pending = forked;
-    }
-    if (bm_bin > 8 && num_rows_in(sp, 8, num_imin(9, bm_bin - 1)) > 0) {
-        const int hi = num_imin(9, bm_bin - 1);
-        const int tmax = 16384;
-        const int grid = num_imin(num_rows_in(sp, 8, hi), sms);
-        if (launch_num_hash<real, 1024, 1024>(ctx, "num_hash_cta1024", grid, (size_t)tmax * slot_bytes, a_rpt,
-                                              a_col, a_val, b_rpt, b_col, b_val, c_rpt64, c_col, c_val, 8, hi, 3,
-                                              tmax) != 0)
-            return -1;
-    }
-    if (bm_bin > 5 && num_rows_in(sp, 5, num_imin(7, bm_bin - 1)) > 0) {
-        const int hi = num_imin(7, bm_bin - 1);
-        const int tmax = 4096;
-        const int grid = num_imin(num_rows_in(sp, 5, hi), (long long)sms * 4);
-        if (launch_num_hash<real, 256, 256>(ctx, "num_hash_cta256", grid, (size_t)tmax * slot_bytes, a_rpt, a_col,
-                                            a_val, b_rpt, b_col, b_val, c_rpt64, c_col, c_val, 5, hi, 2, tmax) != 0)
-            return -1;
-    }
-    if (num_rows_in(sp, 1, num_imin(4, bm_bin - 1)) > 0) {
-        const int hi = num_imin(4, bm_bin - 1);
-        const int tmax = 512;
-        const int grid = num_imin((num_rows_in(sp, 1, hi) + 7) / 8, (long long)sms * 4);
-        if (launch_num_hash<real, 32, 256>(ctx, "num_hash_warp", grid, (size_t)tmax * slot_bytes * 8, a_rpt, a_col,
-                                           a_val, b_rpt, b_col, b_val, c_rpt64, c_col, c_val, 1, hi, 1, tmax) != 0)
-            return -1;
-    }
-    if (num_rows_in(sp, 0, 0) > 0) {
-        const int grid = num_imin((num_rows_in(sp, 0, 0) + 63) / 64, (long long)sms * 8);
-        num_prof_class(ctx, "num_pwarp", 0, 0);
-        num_pwarp_kernel<real><<<grid, 256, 0, ctx->stream>>>(a_rpt, a_col, a_val, b_rpt, b_col, b_val,
-                                                              c_rpt64, c_col, c_val, sp.d_row_perm, sp.d_bins);
-        ctx->prof_end();
-        ctx->launches += 1;
-        NSP_CUDA_TRY(ctx, cudaGetLastError());
+        return 0;
+    };
+    auto launch_light = [&]() -> int {
+        if (bm_bin > 8 && num_rows_in(sp, 8, num_imin(9, bm_bin - 1)) > 0) {
+            const int hi = num_imin(9, bm_bin - 1);
+            const int tmax = 16384;
+            const int grid = num_imin(num_rows_in(sp, 8, hi), sms - push_sms);
+            if (launch_num_hash<real, 1024, 1024>(ctx, "num_hash_cta1024", grid, (size_t)tmax * slot_bytes, a_rpt,
+                                                  a_col, a_val, b_rpt, b_col, b_val, c_rpt64, c_col, c_val, 8, hi, 3,
+                                                  tmax) != 0)
+                return -1;
+        }
+        if (bm_bin > 5 && num_rows_in(sp, 5, num_imin(7, bm_bin - 1)) > 0) {
+            const int hi = num_imin(7, bm_bin - 1);
+            const int tmax = 4096;
+            const int grid = num_imin(num_rows_in(sp, 5, hi), (long long)sms * 4);
+            if (launch_num_hash<real, 256, 256>(ctx, "num_hash_cta256", grid, (size_t)tmax * slot_bytes, a_rpt, a_col,
+                                                a_val, b_rpt, b_col, b_val, c_rpt64, c_col, c_val, 5, hi, 2, tmax) != 0)
+                return -1;
+        }
+        if (num_rows_in(sp, 1, num_imin(4, bm_bin - 1)) > 0) {
+            const int hi = num_imin(4, bm_bin - 1);
+            const int tmax = 512;
+            const int grid = num_imin((num_rows_in(sp, 1, hi) + 7) / 8, (long long)sms * 4);
+            if (launch_num_hash<real, 32, 256>(ctx, "num_hash_warp", grid, (size_t)tmax * slot_bytes * 8, a_rpt, a_col,
+                                               a_val, b_rpt, b_col, b_val, c_rpt64, c_col, c_val, 1, hi, 1, tmax) != 0)
+                return -1;
+        }
+        if (num_rows_in(sp, 0, 0) > 0) {
+            const int grid = num_imin((num_rows_in(sp, 0, 0) + 63) / 64, (long long)sms * 8);
+            num_prof_class(ctx, "num_pwarp", 0, 0);
+            num_pwarp_kernel<real><<<grid, 256, 0, ctx->stream>>>(a_rpt, a_col, a_val, b_rpt, b_col, b_val, c_rpt64, c_col,
+                                                                  c_val, sp.d_row_perm, sp.d_bins, ctx->peer_out);
+            ctx->prof_end();
+            ctx->launches += 1;
+            NSP_CUDA_TRY(ctx, cudaGetLastError());
+        }
+        return 0;
+    };
+    // One GPU: heaviest class first, the light classes fill the tail of the heavy launch.  Multi-GPU: a tile of C
+    // can leave for the peers once ALL rows that overlap it are done, so the (short) light classes go first and
+    // the heavy launch then completes tiles steadily while it runs.
+    if (peers) {
+        if (launch_light() != 0 || launch_bitmap() != 0) return -1;
+    } else {
+        if (launch_bitmap() != 0 || launch_light() != 0) return -1;
     }
     if (sp.join_pending) {
         NSP_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
         sp.join_pending = false;
     }
-    if (ctx->peer_out.n > 0) {
-        // rows the heavy kernel did not push itself: the light classes and the multi-slab rows
-        const int grid = num_imin(((long long)M + 7) / 8, (long long)sms * 16);
-        push_rows_kernel<real><<<grid, 256, 0, ctx->stream>>>(M, a_rpt, c_rpt64, c_col, c_val, bm_bin, kNumShift,
-                                                            num_rows_in(sp, bm_bin, kNumBins - 1) > 0, ctx->peer_out);
-        ctx->launches += 1;
-        NSP_CUDA_TRY(ctx, cudaGetLastError());
-    }
+    if (peers && peer_push_end(ctx) != 0) return -1;
     return 0;
 }
 

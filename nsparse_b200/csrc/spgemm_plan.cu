@@ -375,6 +375,12 @@ int plan_by_count(nsp_context *ctx, int M, int shift, const int *a_rpt, int row0
     cudaStream_t st = ctx->stream;
     const int *row_cnt = sp.d_row_cnt + row0;
     const int *row_ip = sp.d_row_ip + row0;
+    if (sp.join_pending) {
+        // a previous numeric phase left through an error path before joining its side-stream launch, which
+        // still reads d_bins / d_row_perm: order it before they are rewritten
+        NSP_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+        sp.join_pending = false;
+    }
     NSP_CUDA_TRY(ctx, cudaMemsetAsync(sp.d_bins, 0, sizeof(int) * kBinInts, st));
     NSP_CUDA_TRY(ctx, cudaMemsetAsync(sp.d_binsum, 0, sizeof(unsigned long long) * kSumInts, st));
     if (M > 0) {

@@ -2,7 +2,8 @@
 //
 // Reference: set_row_nnz + set_row_nz_bin_* (kernel_spgemm_hash_d.cu:266-622, 1077-1185).
 // What is kept: row-wise Gustavson, rows binned by an upper bound of their size, one hash set
-// per row probed linearly with hash = (col * 107) & (size - 1), table in shared memory.
+// per row probed linearly, table in shared memory (the hash itself is Fibonacci hashing, common.cuh
+// hash_slot, not the reference's (col * 107) & (size - 1): DESIGN.md 4.1).
 // What is re-designed for B200:
 //   * ladder derived from 227 KiB of shared memory: hash sets up to 32768 keys (reference: 8192);
 //     every table is sized per ROW (next pow2 of 4/3 * bound), so clearing it costs what the row
@@ -116,7 +117,8 @@ sym_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
 
 // ---- bitmap class: one CTA per row, one pass over the row's products per column window -----------
 // Window of W = 2^wshift columns (W/8 bytes of shared memory, up to 2^20).  Every product sets its bit
-// with one shared-memory atomicOr in the block-transposed layout (spgemm_device.cuh), the row's count
+// with one shared-memory atomicOr per distinct 32-bit word a lane touches (plain bit order, word pairs XOR-
+// swizzled inside their batch: spgemm_device.cuh bitmap_word32), the row's count
 // is the popcount of the window, taken by the sweep that also clears it for the next row.  With more
 // than one window the sub-range of each B row is found by binary search, so a product is still read
 // exactly once.

@@ -39,10 +39,28 @@ def rmat_edges_numpy(scale: int, n_edges: int, seed: int):
     return src.astype(np.int64), dst.astype(np.int64)
 
 
-def rmat_edges(scale: int, n_edges: int, seed: int):
-    from . import _lib
+_GEN_LIB = None
 
-    L = _lib.load()
+
+def _gen_lib():
+    """libnsparse_gen.so: the generator alone (csrc/gen.cpp, no CUDA), so that generating an input -- in
+    bench.py's reference arm, in the CPU tests -- does not load the product library."""
+    global _GEN_LIB
+    if _GEN_LIB is None:
+        import os
+
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libnsparse_gen.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is not built: run `make lib`")
+        L = C.CDLL(path)
+        L.nsp_gen_rmat_edges.restype = C.c_int
+        L.nsp_gen_rmat_edges.argtypes = [C.c_int, C.c_longlong, C.c_ulonglong, C.c_void_p, C.c_void_p]
+        _GEN_LIB = L
+    return _GEN_LIB
+
+
+def rmat_edges(scale: int, n_edges: int, seed: int):
+    L = _gen_lib()
     src = np.empty(n_edges, dtype=np.int64)
     dst = np.empty(n_edges, dtype=np.int64)
     rc = L.nsp_gen_rmat_edges(scale, n_edges, seed, src.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p))

@@ -185,18 +185,32 @@ class PeerBuffers:
         self.ctx.check(self.ctx.lib.nsp_spgemm_set_peers(self.ctx.handle, len(cols), (C.c_void_p * len(cols))(*cols),
                                                          (C.c_void_p * len(vals))(*vals), elem_offset))
 
+    def check_status(self):
+        import ctypes as C
+
+        err = C.c_int(0)
+        self.ctx.check(self.ctx.lib.nsp_spgemm_peers_status(self.ctx.handle, C.byref(err)))
+
     def clear_fused_targets(self):
         self.ctx.check(self.ctx.lib.nsp_spgemm_set_peers(self.ctx.handle, 0, None, None, 0))
 
     def release(self):
+        """Collective.  Two phases with a barrier in between: every rank first closes the mappings it
+        imported, and only when all ranks have done so are the exported buffers freed (cudaFree of an exported
+        region that an importer still has open is undefined behaviour)."""
         import ctypes as C
+
+        import torch.distributed as dist
 
         self.col = self.val = self.rpt = None
         for p in self._opened:
             self.ctx.lib.nsp_peer_close(self.ctx.handle, C.c_void_p(p))
+        self._opened = []
+        if self._own and dist.is_initialized():
+            dist.barrier(self.group)
         for p in self._own.values():
             self.ctx.lib.nsp_peer_free(self.ctx.handle, C.c_void_p(p))
-        self._own, self._opened = {}, []
+        self._own = {}
         self.cap_nnz = -1
 
     def ensure(self, tot: int, n_rows: int, tdt, dev):
@@ -281,12 +295,13 @@ def spgemm_kernel_hash_mgpu(a_local: CSR, b: CSR, cuts, n_rows: int, total_ip: i
         col, val, rpt = peers.col, peers.val, peers.rpt
         out = (col[lo:max(hi, lo + 1)], val[lo:max(hi, lo + 1)])
         if peers.fused:
-            # the numeric kernels store every entry into all the peers as they produce it
+            # the numeric kernels count finished tiles of C, the pusher kernel sends them to all peers meanwhile
             peers.set_fused_targets(lo)
             try:
                 spgemm_numeric(a_local, b, d_rpt64, nnz, ctx, out=out)
             finally:
                 peers.clear_fused_targets()
+            peers.check_status()
         elif peers.pieces >= 1 and a_local.M > 0:
             # pipeline: piece k+1 is computed while the copy engines carry piece k to the peers
             main = torch.cuda.current_stream(dev)

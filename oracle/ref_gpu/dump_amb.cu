@@ -4,13 +4,18 @@
 // (oracle/Makefile target ref_gpu; `__shfl_xor(` -> `__shfl_xor_sync(0xffffffffu, ` on a temporary
 // copy because the originals do not compile for sm_70+).  Never part of the product.
 //
-//   dump_amb <in.mtx> <seg_size> <block_size> <out.bin>
+//   dump_amb <in.mtx | in.csrbin> <seg_size> <block_size> <out.bin | -> [reps]
+//
+// in.csrbin (any name not ending in .mtx): int32 {M, N, nnz, sizeof(real)}, rpt int32[M+1], col int32[nnz],
+// val real[nnz].  With reps > 0 the SpMV is also timed with the reference's protocol (spmv_amb.cu:45-62: mean
+// of `reps` calls after one warm-up, cudaEvents on stream 0) and one JSON line is printed; "-" skips the dump.
 //
 // out.bin: int32 header {M, N, nnz_csr, pad_M, c_size, nnz_amb, block_size, seg_size, seg_num, sizeof(real)}
 //          then rpt, col, val (CSR as read), cs, cl, sellcs_col, sellcs_val, s_write_permutation,
 //          s_write_permutation_offset, write_permutation, x (N reals), y (M reals)
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <cuda_runtime.h>
 #include <nsparse.h>
 
@@ -40,7 +45,34 @@ int main(int argc, char **argv)
     sfCSR mat;
     sfAMB amb;
     sfPlan plan;
-    init_csr_matrix_from_file(&mat, argv[1]);
+    const size_t alen = strlen(argv[1]);
+    if (alen >= 4 && !strcmp(argv[1] + alen - 4, ".mtx")) {
+        init_csr_matrix_from_file(&mat, argv[1]);
+    } else {
+        FILE *fi = fopen(argv[1], "rb");
+        int h[4];
+        if (!fi || fread(h, sizeof(int), 4, fi) != 4 || h[3] != (int)sizeof(real)) {
+            fprintf(stderr, "%s: cannot read raw CSR (value size must be %d)\n", argv[1], (int)sizeof(real));
+            return 2;
+        }
+        mat.M = h[0];
+        mat.N = h[1];
+        mat.nnz = h[2];
+        mat.nnz_max = 0;
+        mat.matrix_name = argv[1];
+        mat.rpt = (int *)malloc(sizeof(int) * (mat.M + 1));
+        mat.col = (int *)malloc(sizeof(int) * (mat.nnz ? mat.nnz : 1));
+        mat.val = (real *)malloc(sizeof(real) * (mat.nnz ? mat.nnz : 1));
+        if (fread(mat.rpt, sizeof(int), mat.M + 1, fi) != (size_t)mat.M + 1 ||
+            fread(mat.col, sizeof(int), mat.nnz, fi) != (size_t)mat.nnz ||
+            fread(mat.val, sizeof(real), mat.nnz, fi) != (size_t)mat.nnz) {
+            fprintf(stderr, "%s: short file\n", argv[1]);
+            return 2;
+        }
+        fclose(fi);
+        for (int i = 0; i < mat.M; ++i)
+            if (mat.rpt[i + 1] - mat.rpt[i] > mat.nnz_max) mat.nnz_max = mat.rpt[i + 1] - mat.rpt[i];
+    }
     csr_memcpy(&mat);
     init_plan(&plan);
     set_plan(&plan, (size_t)atol(argv[2]), atoi(argv[3]));
@@ -59,6 +91,30 @@ int main(int argc, char **argv)
         fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(e));
         return 3;
     }
+    const int reps = argc > 5 ? atoi(argv[5]) : 0;
+    if (reps > 0) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        double sum = 0, best = 1e30;
+        for (int i = 0; i <= reps; ++i) {
+            cudaEventRecord(e0, 0);
+            sf_spmv_amb(d_y, &amb, d_x, &plan);
+            cudaEventRecord(e1, 0);
+            cudaDeviceSynchronize();
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (i > 0) {
+                sum += ms;
+                if (ms < best) best = ms;
+            }
+        }
+        printf("{\"impl\": \"cuda-c sf_csr2amb + sf_spmv_amb\", \"M\": %d, \"N\": %d, \"nnz\": %d, \"seg_size\": %d, "
+               "\"block_size\": %d, \"reps\": %d, \"ms_mean\": %.6f, \"ms_min\": %.6f, \"gflops\": %.4f, \"value_bytes\": %d}\n",
+               mat.M, mat.N, mat.nnz, (int)amb.seg_size, amb.block_size, reps, sum / reps, best,
+               2.0 * mat.nnz / (sum / reps) / 1e6, (int)sizeof(real));
+    }
+    if (!strcmp(argv[4], "-")) return 0;
     FILE *f = fopen(argv[4], "wb");
     if (!f) {
         perror(argv[4]);
