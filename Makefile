@@ -12,7 +12,7 @@ OBJ       := build/obj
 LIBDIR    := nsparse_b200/lib
 BIN       := bin
 
-CORE_CU   := context peer_push spgemm_plan spgemm_symbolic spgemm_numeric_s spgemm_numeric_d c_api amb_convert amb_spmv amb_api
+CORE_CU   := context peer_push spgemm_plan spgemm_symbolic spgemm_numeric_s spgemm_numeric_d c_api mgpu_api amb_convert amb_spmv amb_api
 CORE_OBJ  := $(addprefix $(OBJ)/,$(addsuffix .o,$(CORE_CU))) $(OBJ)/gen.o $(OBJ)/mtx_reader.o
 
 .PHONY: all lib compat drivers clean oracle
@@ -77,6 +77,8 @@ drivers: compat
 	  $(NVCC) $(DRV_FLAGS) -DDOUBLE $(REF_DIR)/cuda-c/src/sample/spmv/spmv_amb.cu -o $(BIN)/amb_d -L$(LIBDIR) -lnsparse_d -lcusparse -lgomp; \
 	  echo "drivers built from $(REF_DIR) (sources unchanged)"; \
 	else echo "reference tree not present: drivers skipped"; fi
+	$(NVCC) $(DRV_FLAGS) -DFLOAT  $(SRC)/sample/spgemm_hash_mgpu.cu -o $(BIN)/spgemm_hash_mgpu_s -L$(LIBDIR) -lnsparse_s -lcusparse -lgomp
+	$(NVCC) $(DRV_FLAGS) -DDOUBLE $(SRC)/sample/spgemm_hash_mgpu.cu -o $(BIN)/spgemm_hash_mgpu_d -L$(LIBDIR) -lnsparse_d -lcusparse -lgomp
 	@# the same protocol driver that oracle/Makefile builds against the REFERENCE's SpGEMM, linked against this
 	@# library instead (test infrastructure: raw CSR in, reference timing protocol, C out)
 	@mkdir -p oracle/_ref

@@ -152,4 +152,10 @@ void spgemm_kernel_hash(sfCSR *a, sfCSR *b, sfCSR *c);         /* kernel_spgemm_
 void spgemm_cu_csr(sfCSR *a, sfCSR *b, sfCSR *c);              /* comparison answer for the driver's self-check */
 void check_spgemm_answer(sfCSR c, sfCSR ans);                  /* nsparse.cu:300 */
 
+/* ---- multi-GPU extension (not in the reference; does not disturb the symbols above) ------
+ * a, b: HOST CSR; c: array of ngpu sfCSR, c[g].d_* = the full product on GPU g.  Driver:
+ * nsparse_b200/csrc/sample/spgemm_hash_mgpu.cu (bin/spgemm_hash_mgpu_{s,d}). */
+void spgemm_kernel_hash_mgpu(sfCSR *a, sfCSR *b, sfCSR *c, int ngpu);
+void release_csr_mgpu(sfCSR *c, int ngpu);
+
 #endif /* NSPARSE_B200_CONTRACT_H */

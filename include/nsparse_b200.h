@@ -186,6 +186,39 @@ int nsp_spgemm_peers_status(nsp_context *ctx, int *h_error);
 int nsp_push_to_peers(nsp_context *ctx, int npeers, void *const *d_peer_bases, size_t byte_offset,
                       const void *d_src, size_t nbytes);
 
+/* ------------------------------------------------------------------------------------
+ * multi-GPU SpGEMM from ONE process (new; the reference is single GPU, its driver flow is
+ * cuda-c/src/sample/spgemm/spgemm_hash.cu:14-94).  A and B are HOST CSR.  A is cut into ngpu contiguous row
+ * blocks of ~equal intermediate products, B is replicated, one host thread per GPU runs the single-GPU
+ * pipeline on its block and every GPU receives the FULL C (allgatherv over NVLink peer memory, overlapped with
+ * the numeric phase as described at nsp_spgemm_set_peers).  Two phases like the single-GPU entry points, so
+ * that the caller owns C:
+ *   nsp_mgpu_spgemm_symbolic_*   uploads the blocks, symbolic phase on every GPU; returns nnz(C) and the products
+ *   (caller allocates, ON GPU g, d_c_rpt64[g] int64[M+1], d_c_col[g] int32[nnz], d_c_val[g] real[nnz])
+ *   nsp_mgpu_spgemm_numeric_*    numeric phase + gather; returns with every GPU idle and every copy complete
+ * nsp_mgpu_block reports GPU g's rows [row0, row1), its displacement / entry count in C and the wall-clock
+ * milliseconds its host thread spent in the two phases of the last product.  devices == NULL: GPUs 0..ngpu-1;
+ * at most 8 GPUs; all pairs need peer access (NVLink).
+ * ---------------------------------------------------------------------------------- */
+typedef struct nsp_mgpu nsp_mgpu;
+int nsp_mgpu_create(nsp_mgpu **mg, int ngpu, const int *devices);
+int nsp_mgpu_destroy(nsp_mgpu *mg);
+const char *nsp_mgpu_last_error(nsp_mgpu *mg);
+int nsp_mgpu_ngpu(nsp_mgpu *mg);
+nsp_context *nsp_mgpu_context(nsp_mgpu *mg, int g);      /* the per-GPU context (options, nsp_rpt64_to_rpt32, ...) */
+int nsp_mgpu_block(nsp_mgpu *mg, int g, int *device, int *row0, int *row1, long long *elem0, long long *nnz,
+                   double *ms_symbolic, double *ms_numeric);
+int nsp_mgpu_spgemm_symbolic_s(nsp_mgpu *mg, int M, int K, int N,
+                               const int *h_a_rpt, const int *h_a_col, const float *h_a_val,
+                               const int *h_b_rpt, const int *h_b_col, const float *h_b_val,
+                               long long *h_nnz_c, long long *h_intprod);
+int nsp_mgpu_spgemm_symbolic_d(nsp_mgpu *mg, int M, int K, int N,
+                               const int *h_a_rpt, const int *h_a_col, const double *h_a_val,
+                               const int *h_b_rpt, const int *h_b_col, const double *h_b_val,
+                               long long *h_nnz_c, long long *h_intprod);
+int nsp_mgpu_spgemm_numeric_s(nsp_mgpu *mg, long long *const *d_c_rpt64, int *const *d_c_col, float *const *d_c_val);
+int nsp_mgpu_spgemm_numeric_d(nsp_mgpu *mg, long long *const *d_c_rpt64, int *const *d_c_col, double *const *d_c_val);
+
 /* nsp_push_to_peers through an NVSwitch multicast address (NVLS): d_multicast_base is the multicast
  * mapping of the same array on all GPUs; one multimem.st per 16 bytes reaches every copy, the local one
  * included.  Same alignment rules. */

@@ -79,6 +79,17 @@ SIGNATURES = {
     "nsp_copy_async": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
     "nsp_spgemm_set_peers": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), ll]),
     "nsp_spgemm_peers_status": (C.c_int, [vp, C.POINTER(C.c_int)]),
+    "nsp_mgpu_create": (C.c_int, [C.POINTER(vp), C.c_int, vp]),
+    "nsp_mgpu_destroy": (C.c_int, [vp]),
+    "nsp_mgpu_last_error": (C.c_char_p, [vp]),
+    "nsp_mgpu_ngpu": (C.c_int, [vp]),
+    "nsp_mgpu_context": (vp, [vp, C.c_int]),
+    "nsp_mgpu_block": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(ll),
+                                 C.POINTER(ll), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "nsp_mgpu_spgemm_symbolic_s": (C.c_int, [vp, C.c_int, C.c_int, C.c_int] + [vp] * 6 + [C.POINTER(ll), C.POINTER(ll)]),
+    "nsp_mgpu_spgemm_symbolic_d": (C.c_int, [vp, C.c_int, C.c_int, C.c_int] + [vp] * 6 + [C.POINTER(ll), C.POINTER(ll)]),
+    "nsp_mgpu_spgemm_numeric_s": (C.c_int, [vp, vp, vp, vp]),
+    "nsp_mgpu_spgemm_numeric_d": (C.c_int, [vp, vp, vp, vp]),
     "nsp_push_multicast": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t]),
     "nsp_push_to_peers": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.c_size_t, vp, C.c_size_t]),
     "nsp_read_mtx": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(ll),

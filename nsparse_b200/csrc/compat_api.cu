@@ -30,21 +30,30 @@ static_assert(sizeof(sfAMB) == 176, "sfAMB layout (cuda-c/inc/nsparse.h:78-107)"
 
 namespace {
 
-// one lazily created context per process on the current device, legacy default stream: the
-// drivers bracket the calls with events on stream 0 (spgemm_hash.cu:40-44, spmv_amb.cu:47-52)
-nsp_context *the_context()
+// one lazily created context per device of the process, legacy default stream: the drivers bracket the
+// calls with events on stream 0 (spgemm_hash.cu:40-44, spmv_amb.cu:47-52)
+struct DevState {
+    nsp_context *ctx = nullptr;
+    long long *d_rpt64 = nullptr;     // int64 row pointer of the core, narrowed into sfCSR's int d_rpt
+    int rpt64_cap = -1;
+};
+DevState g_dev[64];
+
+DevState &dev_state()
 {
-    static nsp_context *ctx = nullptr;
-    if (!ctx) {
-        int dev = 0;
-        checkCudaErrors(cudaGetDevice(&dev));
-        if (nsp_create(&ctx, dev) != 0) {
+    int dev = 0;
+    checkCudaErrors(cudaGetDevice(&dev));
+    DevState &s = g_dev[dev & 63];
+    if (!s.ctx) {
+        if (nsp_create(&s.ctx, dev) != 0) {
             fprintf(stderr, "nsparse-b200: cannot create a context on device %d (needs a B200, sm_100)\n", dev);
             exit(EXIT_FAILURE);
         }
     }
-    return ctx;
+    return s;
 }
+
+nsp_context *the_context() { return dev_state().ctx; }
 
 void check(int rc, const char *what)
 {
@@ -246,17 +255,17 @@ void get_spgemm_flop(sfCSR *a, sfCSR *b, int M, long long int *flop)
 // int; a product with more than INT_MAX entries aborts with a message (the reference wraps).
 void spgemm_kernel_hash(sfCSR *a, sfCSR *b, sfCSR *c)
 {
-    nsp_context *ctx = the_context();
+    DevState &ds = dev_state();
+    nsp_context *ctx = ds.ctx;
     const int M = a->M, K = a->N, N = b->N;
     c->M = M;
     c->N = N;
-    static long long *d_rpt64 = nullptr;
-    static int rpt64_cap = -1;
-    if (M > rpt64_cap) {
-        cudaFree(d_rpt64);
-        checkCudaErrors(cudaMalloc((void **)&d_rpt64, sizeof(long long) * ((size_t)M + 1)));
-        rpt64_cap = M;
+    if (M > ds.rpt64_cap) {
+        cudaFree(ds.d_rpt64);
+        checkCudaErrors(cudaMalloc((void **)&ds.d_rpt64, sizeof(long long) * ((size_t)M + 1)));
+        ds.rpt64_cap = M;
     }
+    long long *d_rpt64 = ds.d_rpt64;
     long long nnz = 0, ip = 0;
     check(nsp_spgemm_symbolic(ctx, M, K, N, a->d_rpt, a->d_col, b->d_rpt, b->d_col, d_rpt64, &nnz, &ip),
           "spgemm_kernel_hash (symbolic)");
@@ -275,6 +284,86 @@ void spgemm_kernel_hash(sfCSR *a, sfCSR *b, sfCSR *c)
                                        d_rpt64, c->d_col, c->d_val),
           "spgemm_kernel_hash (numeric)");
     check(nsp_sync(ctx), "spgemm_kernel_hash (sync)");
+}
+
+// C = A * B on `ngpu` GPUs of this process (extension; the reference is single GPU).  a, b: HOST CSR (rpt / col /
+// val as init_csr_matrix_from_file leaves them).  c: array of ngpu sfCSR; on return c[g].d_rpt / d_col / d_val
+// hold the FULL product on GPU g (cudaMalloc'ed there, released with release_csr_mgpu), c[g].M / N / nnz are set,
+// and every GPU is idle.  Rows are cut by equal intermediate products, B is replicated, the row blocks of C are
+// gathered over NVLink peer memory while they are computed (nsp_mgpu_*, include/nsparse_b200.h).
+void spgemm_kernel_hash_mgpu(sfCSR *a, sfCSR *b, sfCSR *c, int ngpu)
+{
+    static nsp_mgpu *mg = nullptr;
+    if (mg && nsp_mgpu_ngpu(mg) != ngpu) {
+        nsp_mgpu_destroy(mg);
+        mg = nullptr;
+    }
+    if (!mg && nsp_mgpu_create(&mg, ngpu, nullptr) != 0) {
+        fprintf(stderr, "nsparse-b200: cannot set up %d GPUs with peer access\n", ngpu);
+        exit(EXIT_FAILURE);
+    }
+    auto mcheck = [&](int rc, const char *what) {
+        if (rc != 0) {
+            fprintf(stderr, "nsparse-b200: %s failed (%d): %s\n", what, rc, nsp_mgpu_last_error(mg));
+            exit(EXIT_FAILURE);
+        }
+    };
+    int cur = 0;
+    checkCudaErrors(cudaGetDevice(&cur));
+    const int M = a->M, K = a->N, N = b->N;
+    long long nnz = 0, ip = 0;
+    mcheck(NSP_PREC(nsp_mgpu_spgemm_symbolic)(mg, M, K, N, a->rpt, a->col, a->val, b->rpt, b->col, b->val, &nnz, &ip),
+           "spgemm_kernel_hash_mgpu (symbolic)");
+    if (nnz > (long long)INT_MAX) {
+        fprintf(stderr, "nsparse-b200: nnz(C) = %lld does not fit sfCSR's int nnz; use nsp_mgpu_spgemm_* (64-bit row pointer)\n", nnz);
+        exit(EXIT_FAILURE);
+    }
+    long long *rpt64[8];
+    int *col[8];
+    real *val[8];
+    for (int g = 0; g < ngpu; ++g) {
+        int dev = g;
+        nsp_mgpu_block(mg, g, &dev, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        checkCudaErrors(cudaSetDevice(dev));
+        c[g].M = M;
+        c[g].N = N;
+        c[g].nnz = (int)nnz;
+        c[g].nnz_max = 0;
+        c[g].rpt = nullptr;
+        c[g].col = nullptr;
+        c[g].val = nullptr;
+        checkCudaErrors(cudaMalloc((void **)&rpt64[g], sizeof(long long) * ((size_t)M + 1)));
+        checkCudaErrors(cudaMalloc((void **)&(c[g].d_rpt), sizeof(int) * ((size_t)M + 1)));
+        checkCudaErrors(cudaMalloc((void **)&(c[g].d_col), sizeof(int) * (size_t)(nnz > 0 ? nnz : 1)));
+        checkCudaErrors(cudaMalloc((void **)&(c[g].d_val), sizeof(real) * (size_t)(nnz > 0 ? nnz : 1)));
+        col[g] = c[g].d_col;
+        val[g] = c[g].d_val;
+    }
+    mcheck(NSP_PREC(nsp_mgpu_spgemm_numeric)(mg, rpt64, col, val), "spgemm_kernel_hash_mgpu (numeric)");
+    for (int g = 0; g < ngpu; ++g) {
+        int dev = g;
+        nsp_mgpu_block(mg, g, &dev, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        checkCudaErrors(cudaSetDevice(dev));
+        nsp_context *ctx = nsp_mgpu_context(mg, g);
+        if (nsp_rpt64_to_rpt32(ctx, M, rpt64[g], nnz, c[g].d_rpt) != 0 || nsp_sync(ctx) != 0) {
+            fprintf(stderr, "nsparse-b200: spgemm_kernel_hash_mgpu (row pointer) failed: %s\n", nsp_last_error(ctx));
+            exit(EXIT_FAILURE);
+        }
+        checkCudaErrors(cudaFree(rpt64[g]));
+    }
+    checkCudaErrors(cudaSetDevice(cur));
+}
+
+// release_csr for the array spgemm_kernel_hash_mgpu filled (c[g] lives on GPU g)
+void release_csr_mgpu(sfCSR *c, int ngpu)
+{
+    int cur = 0;
+    checkCudaErrors(cudaGetDevice(&cur));
+    for (int g = 0; g < ngpu; ++g) {
+        checkCudaErrors(cudaSetDevice(g));
+        release_csr(c[g]);
+    }
+    checkCudaErrors(cudaSetDevice(cur));
 }
 
 // ---- AMB SpMV ------------------------------------------------------------------------------------------

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--b", default="self", help="self | er4")
     ap.add_argument("--skip-check", action="store_true")
     ap.add_argument("--phases", action="store_true", help="print the cycles per phase of the heavy numeric kernel")
+    ap.add_argument("--dist", action="store_true", help="print the distribution of rows / entries / products over log2(nnz(C_i))")
     ap.add_argument("--sweep", default="", help="';'-separated option sets 'k=v,k=v' run one after another")
     args = ap.parse_args()
     dt = np.float32 if args.dtype == "f32" else np.float64
@@ -66,6 +67,24 @@ def main():
                   print(f"   {n:20s} {ms:10.3f} ms rows={rows:9d} ip={kip:13d} alen={alen:11d} "
                         f"avgB={kip / max(alen, 1):8.1f}  Gprod/s={kip / max(ms, 1e-9) / 1e6:8.2f}")
           del d_col, d_val, d_rpt64
+    if args.dist:
+        d_rpt64, nnz, ip = ns.spgemm_symbolic(a, b, ctx)
+        cnt = (d_rpt64[1:] - d_rpt64[:-1])
+        blen = (b.d_rpt[1:] - b.d_rpt[:-1]).long()
+        arow = torch.repeat_interleave(torch.arange(a.M, device="cuda"), (a.d_rpt[1:] - a.d_rpt[:-1]).long())
+        rip = torch.zeros(a.M, dtype=torch.int64, device="cuda").index_add_(0, arow, blen[a.d_col.long()])
+        alen = (a.d_rpt[1:] - a.d_rpt[:-1]).long()
+        lb = torch.where(cnt > 0, torch.ceil(torch.log2(cnt.double().clamp_min(1))).long(), torch.full_like(cnt, -1))
+        print("log2(nnz) bin:      rows      nnz(C) share   products share   avg E   avg products/row  avg nnz/row  compression")
+        for bin_ in range(-1, 22):
+            m = lb == bin_
+            n = int(m.sum())
+            if n == 0:
+                continue
+            print(f"  <=2^{bin_:2d}: {n:9d}  {float(cnt[m].sum()) / max(nnz, 1):10.4f}  {float(rip[m].sum()) / max(ip, 1):12.4f}  "
+                  f"{float(alen[m].double().mean()):8.1f}  {float(rip[m].double().mean()):12.0f}  {float(cnt[m].double().mean()):10.0f}  "
+                  f"{float(rip[m].sum()) / max(float(cnt[m].sum()), 1):6.2f}")
+        del d_rpt64
     if args.skip_check:
         return
     # linearity check: C*1 == A*(B*1) in fp64
