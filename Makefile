@@ -75,8 +75,12 @@ drivers: compat
 	  $(NVCC) $(DRV_FLAGS) -DDOUBLE $(REF_DIR)/cuda-c/src/sample/spgemm/spgemm_hash.cu -o $(BIN)/spgemm_hash_d -L$(LIBDIR) -lnsparse_d -lcusparse -lgomp; \
 	  $(NVCC) $(DRV_FLAGS) -DFLOAT  $(REF_DIR)/cuda-c/src/sample/spmv/spmv_amb.cu -o $(BIN)/amb_s -L$(LIBDIR) -lnsparse_s -lcusparse -lgomp; \
 	  $(NVCC) $(DRV_FLAGS) -DDOUBLE $(REF_DIR)/cuda-c/src/sample/spmv/spmv_amb.cu -o $(BIN)/amb_d -L$(LIBDIR) -lnsparse_d -lcusparse -lgomp; \
+	  $(NVCC) $(DRV_FLAGS) -DFLOAT  $(REF_DIR)/cuda-c/src/sample/spgemm/spgemm_cu_csr.cu -o $(BIN)/spgemm_cu_csr_s -L$(LIBDIR) -lnsparse_s -lcusparse -lgomp; \
+	  $(NVCC) $(DRV_FLAGS) -DDOUBLE $(REF_DIR)/cuda-c/src/sample/spgemm/spgemm_cu_csr.cu -o $(BIN)/spgemm_cu_csr_d -L$(LIBDIR) -lnsparse_d -lcusparse -lgomp; \
 	  echo "drivers built from $(REF_DIR) (sources unchanged)"; \
 	else echo "reference tree not present: drivers skipped"; fi
+	$(NVCC) $(DRV_FLAGS) -DFLOAT  $(SRC)/sample/spmv_cu_csr.cu -o $(BIN)/cu_csr_s -L$(LIBDIR) -lnsparse_s -lcusparse -lgomp
+	$(NVCC) $(DRV_FLAGS) -DDOUBLE $(SRC)/sample/spmv_cu_csr.cu -o $(BIN)/cu_csr_d -L$(LIBDIR) -lnsparse_d -lcusparse -lgomp
 	$(NVCC) $(DRV_FLAGS) -DFLOAT  $(SRC)/sample/spgemm_hash_mgpu.cu -o $(BIN)/spgemm_hash_mgpu_s -L$(LIBDIR) -lnsparse_s -lcusparse -lgomp
 	$(NVCC) $(DRV_FLAGS) -DDOUBLE $(SRC)/sample/spgemm_hash_mgpu.cu -o $(BIN)/spgemm_hash_mgpu_d -L$(LIBDIR) -lnsparse_d -lcusparse -lgomp
 	@# the same protocol driver that oracle/Makefile builds against the REFERENCE's SpGEMM, linked against this

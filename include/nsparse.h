@@ -150,6 +150,11 @@ void ans_check(real *csr_ans, real *ans_vec, int N);           /* nsparse.cu:261
 void get_spgemm_flop(sfCSR *a, sfCSR *b, int M, long long int *flop);   /* kernel_spgemm_cu_csr.cu:35 */
 void spgemm_kernel_hash(sfCSR *a, sfCSR *b, sfCSR *c);         /* kernel_spgemm_hash_*.cu:1035 */
 void spgemm_cu_csr(sfCSR *a, sfCSR *b, sfCSR *c);              /* comparison answer for the driver's self-check */
+#ifdef CUSPARSE_H_   /* the cuSPARSE comparison entry points keep the reference's signatures (nsparse.h:160-165, kernel_spmv_cu_csr.cu:9) */
+void spgemm_kernel_cu_csr(sfCSR *a, sfCSR *b, sfCSR *c, cusparseHandle_t *cusparseHandle, cusparseOperation_t *trans_a,
+                          cusparseOperation_t *trans_b, cusparseMatDescr_t *descr_a, cusparseMatDescr_t *descr_b);
+void sf_spmv_cu_csr(real *d_y, sfCSR *mat, real *d_x, cusparseHandle_t *cusparseHandle, cusparseMatDescr_t *descr);
+#endif
 void check_spgemm_answer(sfCSR c, sfCSR ans);                  /* nsparse.cu:300 */
 
 /* ---- multi-GPU extension (not in the reference; does not disturb the symbols above) ------

@@ -49,7 +49,10 @@ int nsp_set_stream(nsp_context *ctx, void *cuda_stream);
 int nsp_sync(nsp_context *ctx);
 /* tuning knobs, mostly for tests and measurements: "sym_bitmap_min" / "num_bitmap_min" (rows above this many
  * products / entries take the bitmap kernels), "sym_window_shift" / "num_window_shift" (log2 of the bitmap window),
- * "num_cap" (upper limit of the accumulator chunk), "no_vec" (no 128-bit loads of B.col), "no_fork" (long rows on
+ * "num_cap" (upper limit of the accumulator chunk), "sort" (0: the numeric
+ * phase may leave the columns of a row unsorted -- SpGEMM_Hash_Numeric<sort = false> of cuda-cpp/inc/HashSpGEMM_volta.hpp:
+ * 1018-1031; the hash classes then skip their per-row sort, the bitmap class is sorted by construction), "push_sms",
+ * "no_seg", "no_vec" (no 128-bit loads of B.col), "no_fork" (long rows on
  * the main stream), "profile", "debug", "phase_timing" */
 int nsp_set_option(nsp_context *ctx, const char *name, long long value);
 /* With option "profile" = 1 every row-class kernel launch is bracketed by CUDA events on the

@@ -111,6 +111,8 @@ int nsp_set_option(nsp_context *ctx, const char *name, long long value)
     else if (!strcmp(name, "no_fork")) ctx->opt_no_fork = value;
     else if (!strcmp(name, "num_cap")) ctx->opt_num_cap = value;
     else if (!strcmp(name, "push_sms")) ctx->opt_push_sms = value;
+    else if (!strcmp(name, "no_seg")) ctx->opt_no_seg = value;
+    else if (!strcmp(name, "sort")) ctx->opt_unsorted = value == 0;
     else if (!strcmp(name, "phase_timing")) {
         // value 1: start accumulating; value 2: print the totals (cycles summed over CTAs) and reset
         if (value == 2 && ctx->d_phase) {
@@ -366,6 +368,13 @@ int nsp_profile_dump(nsp_context *ctx, char *buf, size_t buflen)
             }
         }
         char line[256];
+        if (i > 0 && ctx->prof[i - 1].name == r.name + "_long") {
+            // the main launch's own duration next to the span of the class
+            float own = 0.f;
+            cudaEventElapsedTime(&own, r.e0, r.e1);
+            snprintf(line, sizeof(line), "%s_own %.6f %lld %lld %lld %lld\n", r.name.c_str(), own, r.rows, r.ip, r.alen, r.out);
+            out += line;
+        }
         snprintf(line, sizeof(line), "%s %.6f %lld %lld %lld %lld\n", r.name.c_str(), ms, r.rows, r.ip, r.alen, r.out);
         out += line;
     }

@@ -21,15 +21,25 @@
         }                                                                                          \
     } while (0)
 
-void spgemm_cu_csr(sfCSR *a, sfCSR *b, sfCSR *c)
-{
 #ifdef FLOAT
-    const cudaDataType dt = CUDA_R_32F;
+static const cudaDataType dt = CUDA_R_32F;
 #else
-    const cudaDataType dt = CUDA_R_64F;
+static const cudaDataType dt = CUDA_R_64F;
 #endif
-    cusparseHandle_t h;
-    CHECK_CUSPARSE(cusparseCreate(&h));
+
+// spgemm_kernel_cu_csr (kernel_spgemm_cu_csr.cu:59-160): C = A * B with cuSPARSE, result left ON THE DEVICE in
+// c->d_rpt / d_col / d_val (cudaMalloc'ed here, released by the caller with release_csr), c->M / N / nnz set.  Same
+// signature as the reference so that its UNCHANGED driver cuda-c/src/sample/spgemm/spgemm_cu_csr.cu builds against
+// this library (bin/spgemm_cu_csr_{s,d}); the legacy descriptors / operations it passes are accepted and ignored
+// (general matrices, no transposition -- what the driver sets), the work is done by the generic cusparseSpGEMM API.
+void spgemm_kernel_cu_csr(sfCSR *a, sfCSR *b, sfCSR *c, cusparseHandle_t *cusparseHandle, cusparseOperation_t *trans_a,
+                          cusparseOperation_t *trans_b, cusparseMatDescr_t *descr_a, cusparseMatDescr_t *descr_b)
+{
+    (void)trans_a;
+    (void)trans_b;
+    (void)descr_a;
+    (void)descr_b;
+    cusparseHandle_t h = *cusparseHandle;
     c->M = a->M;
     c->N = b->N;
     cusparseSpMatDescr_t A, B, C;
@@ -58,12 +68,33 @@ void spgemm_cu_csr(sfCSR *a, sfCSR *b, sfCSR *c)
                                           b2));
     int64_t rows = 0, cols = 0, nnz = 0;
     CHECK_CUSPARSE(cusparseSpMatGetSize(C, &rows, &cols, &nnz));
+    if (nnz > 0x7fffffffll) {
+        fprintf(stderr, "spgemm_kernel_cu_csr: nnz(C) = %lld does not fit sfCSR\n", (long long)nnz);
+        exit(EXIT_FAILURE);
+    }
     c->nnz = (int)nnz;
     checkCudaErrors(cudaMalloc((void **)&c->d_col, sizeof(int) * (size_t)(nnz ? nnz : 1)));
     checkCudaErrors(cudaMalloc((void **)&c->d_val, sizeof(real) * (size_t)(nnz ? nnz : 1)));
     CHECK_CUSPARSE(cusparseCsrSetPointers(C, c->d_rpt, c->d_col, c->d_val));
     CHECK_CUSPARSE(cusparseSpGEMM_copy(h, op, op, &alpha, A, B, &beta, C, dt, CUSPARSE_SPGEMM_DEFAULT, desc));
+    cusparseSpGEMM_destroyDescr(desc);
+    cusparseDestroySpMat(A);
+    cusparseDestroySpMat(B);
+    cusparseDestroySpMat(C);
+    cudaFree(b1);
+    cudaFree(b2);
+    checkCudaErrors(cudaDeviceSynchronize());
+}
 
+// spgemm_cu_csr (kernel_spgemm_cu_csr.cu:162-203): the comparison answer of the hash driver's self-check, rows
+// sorted by column, left on the HOST.
+void spgemm_cu_csr(sfCSR *a, sfCSR *b, sfCSR *c)
+{
+    cusparseHandle_t h;
+    CHECK_CUSPARSE(cusparseCreate(&h));
+    cusparseOperation_t op = CUSPARSE_OPERATION_NON_TRANSPOSE;
+    spgemm_kernel_cu_csr(a, b, c, &h, &op, &op, nullptr, nullptr);
+    const long long nnz = c->nnz;
     // sort every row by column (check_spgemm_answer compares col[] element-wise)
     if (nnz > 0) {
         size_t sb = 0;
@@ -93,11 +124,36 @@ void spgemm_cu_csr(sfCSR *a, sfCSR *b, sfCSR *c)
     }
     csr_memcpyDtH(c);
     release_csr(*c);
-    cusparseSpGEMM_destroyDescr(desc);
-    cusparseDestroySpMat(A);
-    cusparseDestroySpMat(B);
-    cusparseDestroySpMat(C);
     cusparseDestroy(h);
-    cudaFree(b1);
-    cudaFree(b2);
+}
+
+// sf_spmv_cu_csr (kernel_spmv_cu_csr.cu:9-31): y = A x with cuSPARSE; the reference calls the legacy
+// cusparse{S,D}csrmv, which CUDA 12 no longer has -- same signature, generic cusparseSpMV underneath.  The SpMV
+// buffer is kept between calls (the comparison driver times 100 of them).
+void sf_spmv_cu_csr(real *d_y, sfCSR *mat, real *d_x, cusparseHandle_t *cusparseHandle, cusparseMatDescr_t *descr)
+{
+    (void)descr;
+    static void *buf = nullptr;
+    static size_t buf_bytes = 0;
+    const real alpha = (real)1, beta = (real)0;
+    cusparseSpMatDescr_t A;
+    cusparseDnVecDescr_t x, y;
+    CHECK_CUSPARSE(cusparseCreateCsr(&A, mat->M, mat->N, mat->nnz, mat->d_rpt, mat->d_col, mat->d_val, CUSPARSE_INDEX_32I,
+                                     CUSPARSE_INDEX_32I, CUSPARSE_INDEX_BASE_ZERO, dt));
+    CHECK_CUSPARSE(cusparseCreateDnVec(&x, mat->N, d_x, dt));
+    CHECK_CUSPARSE(cusparseCreateDnVec(&y, mat->M, d_y, dt));
+    size_t need = 0;
+    CHECK_CUSPARSE(cusparseSpMV_bufferSize(*cusparseHandle, CUSPARSE_OPERATION_NON_TRANSPOSE, &alpha, A, x, &beta, y, dt,
+                                           CUSPARSE_SPMV_ALG_DEFAULT, &need));
+    if (need > buf_bytes) {
+        cudaFree(buf);
+        checkCudaErrors(cudaMalloc(&buf, need));
+        buf_bytes = need;
+    }
+    CHECK_CUSPARSE(cusparseSpMV(*cusparseHandle, CUSPARSE_OPERATION_NON_TRANSPOSE, &alpha, A, x, &beta, y, dt,
+                                CUSPARSE_SPMV_ALG_DEFAULT, buf));
+    cusparseDestroySpMat(A);
+    cusparseDestroyDnVec(x);
+    cusparseDestroyDnVec(y);
+    checkCudaErrors(cudaDeviceSynchronize());
 }

@@ -1,6 +1,10 @@
 // nsparse-b200: context life cycle and the workspace arena.
 #include "context.h"
 
+#include <stdlib.h>
+
+#include "../../include/nsparse_b200.h"
+
 int nsp_context::arena_reserve(size_t total_bytes)
 {
     if (total_bytes <= arena_bytes) return 0;
@@ -73,6 +77,21 @@ int context_create(nsp_context **out, int device)
             cudaGetLastError();
         }
     }
+    // NSP_OPTIONS="name=value,name=value": nsp_set_option for processes that cannot call it (the unchanged sample
+    // drivers under compute-sanitizer, forced windows x chunks x slabs cases)
+    if (const char *env = getenv("NSP_OPTIONS")) {
+        std::string e(env);
+        size_t pos = 0;
+        while (pos < e.size()) {
+            size_t end = e.find(',', pos);
+            if (end == std::string::npos) end = e.size();
+            const std::string kv = e.substr(pos, end - pos);
+            const size_t eq = kv.find('=');
+            if (eq != std::string::npos && nsp_set_option(ctx, kv.substr(0, eq).c_str(), atoll(kv.c_str() + eq + 1)) != 0)
+                fprintf(stderr, "nsparse_b200: NSP_OPTIONS: unknown option '%s'\n", kv.substr(0, eq).c_str());
+            pos = end + 1;
+        }
+    }
     *out = ctx;
     return 0;
 }
@@ -93,6 +112,7 @@ int context_destroy(nsp_context *ctx)
         cudaEventDestroy(ctx->ev_push_join);
     }
     cudaFree(ctx->d_push_ws);
+    cudaFree(ctx->d_seg);
     if (ctx->mem_pool) cudaMemPoolDestroy(ctx->mem_pool);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);

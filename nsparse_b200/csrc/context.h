@@ -23,6 +23,7 @@ struct nsp_spgemm_state {
     long long *h_scalars = nullptr;   // pinned mirror
     bool symbolic_done = false;
     long long b_nnz = 0;          // nnz(B) = B.rpt[K], read back by the symbolic plan
+    long long a_nnz = 0;          // entries of A (sum of the row lengths seen by the symbolic plan)
     bool join_pending = false;    // the side-stream launch of this phase has not been joined yet
     bool has_multi_slab = true;   // some row of A has more than 1024 entries (second launch of the heavy numeric kernel)
     bool b_sorted = true;         // rows of B column-sorted (checked by the symbolic plan)
@@ -68,6 +69,12 @@ struct nsp_context {
     char *arena = nullptr;
     size_t arena_bytes = 0;
     size_t arena_used = 0;
+
+    // window cuts per entry of A for the segment mode of the heavy numeric kernel (spgemm_plan.cu)
+    int *d_seg = nullptr;
+    size_t seg_cap = 0;
+    long long opt_unsorted = 0;          // 1: sort = false numeric mode, the hash classes skip the per-row column sort
+    long long opt_no_seg = 0;            // 1: never use the segment mode (tests, A/B measurements)
 
     // options (nsp_set_option)
     long long opt_sym_bitmap_min = -1;   // rows with min(ip,N) >  this go to the bitmap kernel (-1: default)

@@ -162,8 +162,13 @@ struct PartScratch {
     int pre1[BS / 32]; // pre[32 * i]: bank-conflict-free first level of the entry search
     int kb[BS];        // first product of the entry's current segment in B.col / B.val
     int len[BS];       // products of the segment
-    int cur[BS];       // cursor: first product of the entry not yet consumed by the value chunks
-    int end[BS];       // end of the entry's segment in the current column window
+    union {
+        struct {
+            int cur[BS];   // cursor: first product of the entry not yet consumed by the value chunks
+            int end[BS];   // end of the entry's segment in the current column window
+        };
+        int tab[2 * BS];   // segment mode: tab[k * E + e] = first product of entry e at or beyond chunk boundary k
+    };
     real av[BS];       // a_ij (numeric only)
     int wtot[BS / 32 + 1];
 };
@@ -319,6 +324,117 @@ __device__ __forceinline__ int stage_chunk(int t, int E, int glog, const int *__
             s.kb[e] = lo;
             s.len[e] = res - lo;
             s.cur[e] = res;
+        }
+    }
+    __syncthreads();
+    return scan_parts<BS, real>(t, t < E ? s.kb[t] : 0, t < E ? s.len[t] : 0, s);
+}
+
+// ---- segment mode (B column-sorted, at most 4 windows): the window cuts of every B row are PRECOMPUTED per
+// entry of A by entry_segments_kernel (spgemm_plan.cu): seg[w * stride + j] = first product of entry j's B row at
+// or beyond column w << wshift (w = 0: the row's start, w = nwin: its end).  A window stage is then two coalesced
+// loads per entry instead of the dependent chain a_col -> B.rpt -> search probes of stage_window, which was pure
+// exposed latency at the start of every window (profiles/r2_phase_cycles_num_bitmap_s20_baseline.txt: "mark
+// stage" 7 % of the kernel).
+template <int BS, bool kLoadVal, typename real>
+__device__ __forceinline__ int stage_window_seg(int t, int a_beg, int E, const real *__restrict__ a_val,
+                                                const int *__restrict__ seg, long long stride, int win, bool first,
+                                                PartScratch<BS, real> &s)
+{
+    int lo = 0, hi = 0;
+    if (t < E) {
+        lo = ld_nc(seg + (long long)win * stride + a_beg + t);
+        hi = ld_nc(seg + (long long)(win + 1) * stride + a_beg + t);
+        s.kb[t] = lo;
+        s.len[t] = hi - lo;
+        if (kLoadVal && first) s.av[t] = ld_stream(a_val + a_beg + t);
+    }
+    return scan_parts<BS, real>(t, lo, hi - lo, s);
+}
+
+// the same for one slab of a row with more than BS entries
+template <int BS, bool kLoadVal, typename real>
+__device__ __forceinline__ int stage_slab_seg(int t, int base, int a_end, const real *__restrict__ a_val,
+                                              const int *__restrict__ seg, long long stride, int win,
+                                              PartScratch<BS, real> &s)
+{
+    int lo = 0, hi = 0;
+    if (base + t < a_end) {
+        lo = ld_nc(seg + (long long)win * stride + base + t);
+        hi = ld_nc(seg + (long long)(win + 1) * stride + base + t);
+        if (kLoadVal) s.av[t] = ld_stream(a_val + base + t);
+    }
+    s.kb[t] = lo;
+    s.len[t] = hi - lo;
+    return scan_parts<BS, real>(t, lo, hi - lo, s);
+}
+
+// All chunk boundaries of a window at once: tab[k * E + e], k = 0 .. nch, from the staged window segments
+// (s.kb / s.len) and the boundary columns bound[1 .. nch-1].  E * (nch - 1) independent searches run side by
+// side (2^q lanes each), so the window pays ONE chain of dependent probes instead of one per chunk
+// (stage_chunk: "chunk stage" 10 % of the kernel).  Needs E * (nch + 1) <= 2 * BS.  Ends with a barrier.
+template <int BS, typename real>
+__device__ __forceinline__ void build_chunk_table(int t, int E, int nch, const int *__restrict__ b_col,
+                                                  const int *bound, PartScratch<BS, real> &s)
+{
+    const int lane = t & 31;
+    if (t < E) {
+        s.tab[t] = s.kb[t];
+        s.tab[nch * E + t] = s.kb[t] + s.len[t];
+    }
+    const int S = E * (nch - 1);
+    int q = 0;
+    while (q < 5 && (S << (q + 1)) <= BS) ++q;
+    for (int base = 0; base < S; base += BS >> q) {
+        const int sidx = base + (t >> q);
+        int lo = 0, hi = 0, key = 0, e = 0, k = 0;
+        if (sidx < S) {
+            k = sidx / E + 1;
+            e = sidx - (k - 1) * E;
+            lo = s.kb[e];
+            hi = lo + s.len[e];
+            key = bound[k];
+        }
+        const int res = group_lower_bound(b_col, lo, hi, key, q, lane);
+        if (sidx < S && (t & ((1 << q) - 1)) == 0) s.tab[k * E + e] = res;
+    }
+    __syncthreads();
+}
+
+// chunk k of the window from the table
+template <int BS, typename real>
+__device__ __forceinline__ int stage_chunk_tab(int t, int E, int k, PartScratch<BS, real> &s)
+{
+    int lo = 0, hi = 0;
+    if (t < E) {
+        lo = s.tab[k * E + t];
+        hi = s.tab[(k + 1) * E + t];
+        s.kb[t] = lo;
+        s.len[t] = hi - lo;
+    }
+    return scan_parts<BS, real>(t, lo, hi - lo, s);
+}
+
+// chunk [col_lo, col_hi) of the window when the table does not fit: both ends searched in the window segment,
+// which is re-read from the precomputed cuts (first / last: that end is the window's)
+template <int BS, typename real>
+__device__ __forceinline__ int stage_chunk_seg(int t, int a_beg, int E, int glog, const int *__restrict__ b_col,
+                                               const int *__restrict__ seg, long long stride, int win, int col_lo,
+                                               int col_hi, bool first, bool last, PartScratch<BS, real> &s)
+{
+    const int e = t >> glog;
+    if (((t & ~31) >> glog) < E) {
+        int wl = 0, wh = 0;
+        if (e < E) {
+            wl = ld_nc(seg + (long long)win * stride + a_beg + e);
+            wh = ld_nc(seg + (long long)(win + 1) * stride + a_beg + e);
+        }
+        int lo = wl, hi = wh;
+        if (!first) lo = group_lower_bound(b_col, wl, wh, col_lo, glog, t & 31);
+        if (!last) hi = group_lower_bound(b_col, lo, wh, col_hi, glog, t & 31);
+        if (e < E && (t & ((1 << glog) - 1)) == 0) {
+            s.kb[e] = lo;
+            s.len[e] = hi - lo;
         }
     }
     __syncthreads();

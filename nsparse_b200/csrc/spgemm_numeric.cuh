@@ -89,12 +89,13 @@ num_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                 const int *__restrict__ b_col, const real *__restrict__ b_val,
                 const long long *__restrict__ c_rpt, int *__restrict__ c_col, real *__restrict__ c_val,
                 const int *__restrict__ row_perm, int *__restrict__ bins, int bin_lo, int bin_hi,
-                int queue, int tmax, const __grid_constant__ PeerOut peer)
+                int queue, int tmax, int sorted, const __grid_constant__ PeerOut peer)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NG = BS / GROUP;
     __shared__ FlatScratch<GROUP, real> s_flat[NG];
     __shared__ int s_row;
+    __shared__ int s_fill[NG];
     const int g = threadIdx.x / GROUP, t = threadIdx.x % GROUP;
     // values first (8-byte aligned for fp64), then keys
     real *vals = reinterpret_cast<real *>(smem_raw) + (size_t)g * tmax;
@@ -127,11 +128,25 @@ num_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
         for_each_product<GROUP, true, real>(t, a_rpt[rid], a_rpt[rid + 1], a_col, a_val, b_rpt, b_col, b_val,
                                             s_flat[g],
                                             [&](int c, real v) { hash_accumulate(keys, vals, mask, c, v); });
+        if (t == 0) s_fill[g] = 0;
         group_sync<GROUP>();
-        bitonic_sort_slots<GROUP, real>(keys, vals, tsize, t);
-        for (int i = t; i < nnz; i += GROUP) {
-            c_col[off + i] = keys[i];
-            c_val[off + i] = vals[i];
+        if (sorted) {
+            bitonic_sort_slots<GROUP, real>(keys, vals, tsize, t);
+            for (int i = t; i < nnz; i += GROUP) {
+                c_col[off + i] = keys[i];
+                c_val[off + i] = vals[i];
+            }
+        } else {
+            // sort = false (cuda-cpp/inc/HashSpGEMM_volta.hpp:508-605, 1018-1031): the occupied slots are compacted in
+            // table order, columns of a row come out unsorted
+            for (int i = t; i < tsize; i += GROUP) {
+                const int key = keys[i];
+                if (key != kEmptyKey) {
+                    const int pos = atomicAdd(&s_fill[g], 1);
+                    c_col[off + pos] = key;
+                    c_val[off + pos] = vals[i];
+                }
+            }
         }
         group_sync<GROUP>();
         if (peer.n > 0 && t == 0) tiles_done(peer, off, nnz);
@@ -169,15 +184,17 @@ __device__ __forceinline__ int select32(unsigned x, int n)
     return __ffs((int)x) - 1;
 }
 
-// kSorted: the rows of B are column-sorted (checked once per call on the device); otherwise -- the
-// reference reader leaves the rows of symmetric files unsorted (nsparse.cu:115-123) -- every pass walks
-// the whole B rows and filters by column range.
+// kMode: 0 -- the rows of B are NOT column-sorted (the reference reader leaves the rows of symmetric files
+// unsorted, nsparse.cu:115-123; checked once per call on the device): every pass walks the whole B rows and
+// filters by column range; 1 -- sorted, window / chunk cuts found by searching with a cursor per entry;
+// 2 -- sorted and at most 4 windows: the window cuts are precomputed per entry of A (seg, see
+// stage_window_seg) and the chunk cuts of a window are searched all at once (build_chunk_table).
 // kPeers: the fused allgatherv variant (multi-GPU, see PeerOut); a separate instantiation so that the
 // single-GPU kernel carries none of its code (with a run-time test only, the mere presence of the peer
 // loops cost the single-GPU kernel 25 % -- register allocation of the hot loops).
 // kMulti: the instantiation for the rows with more than BS entries of A (red.global mode); the other one
 // skips them and vice versa -- two launches over the same class, so that neither carries the other's code.
-template <typename real, int BS, bool kSorted, bool kPeers, bool kMulti>
+template <typename real, int BS, int kMode, bool kPeers, bool kMulti>
 __global__ void __launch_bounds__(BS, 1)
 num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                   const real *__restrict__ a_val, const int *__restrict__ b_rpt,
@@ -185,10 +202,12 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                   const long long *__restrict__ c_rpt, int *__restrict__ c_col, real *__restrict__ c_val,
                   const int *__restrict__ row_perm, int *__restrict__ bins, int bin_lo, int bin_hi,
                   int queue, int N, int wshift, int cap, int b_vec_end, int dbg, long long *phase_cycles,
-                  const __grid_constant__ PeerOut peer)
+                  const int *__restrict__ seg, long long seg_stride, const __grid_constant__ PeerOut peer)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = BS / 32;
+    constexpr bool kSorted = kMode != 0;
+    constexpr bool kSeg = kMode == 2;
     static_assert(NW == 32, "the batch scan and the entry search assume 32 warps");
     // development aid (build with -DNSP_PHASE_TIMING, nsp_set_option "phase_timing"): thread 0 charges the
     // cycles between barriers to twelve phases and adds them to phase_cycles[] at the end
@@ -210,7 +229,6 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
 #define PH(i)
 #endif
     __shared__ PartScratch<BS, real> s_part;
-    __shared__ int s_row;
     __shared__ int s_batch[kMaxBatches + 1];    // outputs before the batch (exclusive), window relative
     __shared__ int s_bound[kMaxChunks + 1];
     const unsigned W = 1u << wshift;
@@ -226,21 +244,52 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
     class_range(bins, bin_lo, bin_hi, lo, hi);
     const int n = hi - lo;
     const int nwin = (int)(((unsigned)N + W - 1u) >> wshift);
+    // Row queue with a look-ahead of one row: while the CTA works on a row, thread 0 claims the next one and walks
+    // the dependent chain queue -> row_perm -> A.rpt / C.rpt one step per phase (every step consumes a value whose
+    // load was issued a phase earlier), so that a row starts from shared memory instead of four global round trips.
+    __shared__ int s_nrid, s_nab, s_nae;
+    __shared__ long long s_nout;
+    int nx_rid = -1, nx_ab = 0, nx_ae = 0;
+    long long nx_out = 0;
+    if (t == 0) {
+        const int r = atomicAdd(&bins[kBinQueue + queue], 1);
+        if (r < n) {
+            nx_rid = row_perm[lo + r];
+            nx_ab = a_rpt[nx_rid];
+            nx_ae = a_rpt[nx_rid + 1];
+            nx_out = c_rpt[nx_rid];
+        }
+        s_nrid = nx_rid;
+        s_nab = nx_ab;
+        s_nae = nx_ae;
+        s_nout = nx_out;
+    }
     while (true) {
-        if (t == 0) s_row = atomicAdd(&bins[kBinQueue + queue], 1);
         __syncthreads();
-        const int r = s_row;
-        if (r >= n) break;
-        const int rid = row_perm[lo + r];
-        const int a_beg = a_rpt[rid], a_end = a_rpt[rid + 1];
+        const int rid = s_nrid;
+        if (rid < 0) break;
+        const int a_beg = s_nab, a_end = s_nae;
         const int E = a_end - a_beg;
-        if ((E > BS) != kMulti) {                  // the other launch's row (CTA uniform)
-            __syncthreads();                       // everyone has read s_row before thread 0 claims again
+        long long out = s_nout;
+        __syncthreads();                           // everyone has read the slot before thread 0 refills it
+        int nx_r = 0;
+        if ((E > BS) != kMulti) {                  // the other launch's row (CTA uniform): claim the next one at once
+            if (t == 0) {
+                nx_r = atomicAdd(&bins[kBinQueue + queue], 1);
+                nx_rid = -1;
+                if (nx_r < n) {
+                    nx_rid = row_perm[lo + nx_r];
+                    s_nab = a_rpt[nx_rid];
+                    s_nae = a_rpt[nx_rid + 1];
+                    s_nout = c_rpt[nx_rid];
+                }
+                s_nrid = nx_rid;
+            }
             continue;
         }
+        if (t == 0) nx_r = atomicAdd(&bins[kBinQueue + queue], 1);      // step A: claim
         constexpr bool one_slab = !kMulti;
         const int glog = entry_group_log(E, BS);
-        long long out = c_rpt[rid];
         for (int win = 0; win < nwin; ++win) {
             const int c0 = (int)((unsigned)win << wshift);
             const int c1 = (int)min((unsigned)N, (unsigned)c0 + W);
@@ -255,19 +304,24 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
             int staged_total = 0;
             const unsigned ncols = (unsigned)(c1 - c0);
             if (one_slab) {
-                staged_total = stage_window<BS, true, real>(t, a_beg, E, glog, a_col, a_val, b_rpt, b_col, c1,
-                                                            win == 0 || !kSorted, cut_hi, s_part);
+                if (kSeg)
+                    staged_total = stage_window_seg<BS, true, real>(t, a_beg, E, a_val, seg, seg_stride, win, win == 0, s_part);
+                else
+                    staged_total = stage_window<BS, true, real>(t, a_beg, E, glog, a_col, a_val, b_rpt, b_col, c1,
+                                                                win == 0 || !kSorted, cut_hi, s_part);
                 PH(1);
                 run_parts_mark<BS, !kSorted, real>(t, staged_total, b_col, b_vec_end, s_part, bm32, c0, ncols);
                 PH(2);
             } else {
                 for (int base = a_beg; base < a_end; base += BS) {
-                    const int total = stage_parts_range<BS, false, real>(t, base, a_end, a_col, a_val, b_rpt, b_col, c0,
-                                                                         c1, cut_lo, cut_hi, s_part);
+                    const int total = kSeg ? stage_slab_seg<BS, false, real>(t, base, a_end, a_val, seg, seg_stride, win, s_part)
+                                           : stage_parts_range<BS, false, real>(t, base, a_end, a_col, a_val, b_rpt, b_col, c0,
+                                                                                c1, cut_lo, cut_hi, s_part);
                     run_parts_mark<BS, !kSorted, real>(t, total, b_col, b_vec_end, s_part, bm32, c0, ncols);
                     PH(2);
                 }
             }
+            if (t == 0 && win == 0) nx_rid = nx_r < n ? row_perm[lo + nx_r] : -1;          // step B: which row
             // ---- rank: per-word prefixes inside every batch (four batches in flight per warp: the scan is
             //      a chain of five dependent shuffles), batch totals, exclusive scan of the totals by warp 0 ----
             for (int b0 = wid * 4; b0 < nbatch; b0 += NW * 4) {
@@ -298,6 +352,11 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
             }
             __syncthreads();
             PH(3);
+            if (t == 0 && win == 0 && nx_rid >= 0) {                                     // step C: its extent
+                nx_ab = a_rpt[nx_rid];
+                nx_ae = a_rpt[nx_rid + 1];
+                nx_out = c_rpt[nx_rid];
+            }
             if (wid == 0) {
                 // nbatch <= 256: lane l owns the batches 8l .. 8l+7 (nbatch is a multiple of 32)
                 const int per = nbatch >> 5;
@@ -343,6 +402,9 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                 }
             }
             __syncthreads();
+            // segment mode: every chunk cut of the window in one round of searches
+            const bool tab_ok = kSeg && one_slab && nch > 1 && E * (nch + 1) <= 2 * BS;
+            if (tab_ok) build_chunk_table<BS, real>(t, E, nch, b_col, s_bound, s_part);
             PH(4);
             // ---- chunk by chunk ----
             // Rows whose A entries fit one slab: acc[0..cnt) is zeroed, every product of the chunk's column
@@ -370,11 +432,18 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                     atomicAdd(acc + idx, v);
                 };
                 int total = staged_total;                  // one chunk (or unsorted B): the mark pass staged it
-                if (kSorted && nch > 1)
+                if (kSeg && nch > 1)
+                    total = tab_ok ? stage_chunk_tab<BS, real>(t, E, k, s_part)
+                                   : stage_chunk_seg<BS, real>(t, a_beg, E, glog, b_col, seg, seg_stride, win, col_lo, col_hi,
+                                                               k == 0, k == nch - 1, s_part);
+                else if (kSorted && nch > 1)
                     total = stage_chunk<BS, real>(t, E, glog, b_col, col_hi, k == nch - 1, s_part);
                 else
                     __syncthreads();
                 PH(7);
+                // (a variant that issued the rank lookups, accumulator reads and compare-and-swaps of four products
+                // side by side instead of one LDS / FADD / ATOMS.CAST.SPIN chain per product measured 8 % SLOWER:
+                // profiles/r2_ab_value_pass_batched_cas_vs_spin_s20.txt)
                 run_parts<BS, true, real>(t, total, b_col, b_val, s_part, add);
                 PH(8);
                 real *cv = c_val + out + r0;
@@ -438,8 +507,9 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                 };
                 for (int base = a_beg; base < a_end; base += BS) {
                     // (the barriers of the staging order the zero fill before the adds)
-                    const int total = stage_parts_range<BS, true, real>(t, base, a_end, a_col, a_val, b_rpt, b_col, c0, c1,
-                                                                        cut_lo, cut_hi, s_part);
+                    const int total = kSeg ? stage_slab_seg<BS, true, real>(t, base, a_end, a_val, seg, seg_stride, win, s_part)
+                                           : stage_parts_range<BS, true, real>(t, base, a_end, a_col, a_val, b_rpt, b_col, c0, c1,
+                                                                               cut_lo, cut_hi, s_part);
                     run_parts<BS, true, real>(t, total, b_col, b_val, s_part, add_red);
                     PH(10);
                 }
@@ -451,6 +521,12 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                 }
             }
             out += tile_nnz;
+        }
+        if (t == 0) {                                                                     // step D: hand over
+            s_nrid = nx_rid;
+            s_nab = nx_ab;
+            s_nae = nx_ae;
+            s_nout = nx_out;
         }
     }
 #ifdef NSP_PHASE_TIMING
@@ -507,7 +583,7 @@ static int launch_num_hash(nsp_context *ctx, const char *name, int grid, size_t 
     auto kern = num_hash_kernel<real, GROUP, BS>;
     NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     num_prof_class(ctx, name, bin_lo, bin_hi);
-    kern<<<grid, BS, smem, ctx->stream>>>(NSP_NUM_ARGS, bin_lo, bin_hi, queue, tmax, ctx->peer_out);
+    kern<<<grid, BS, smem, ctx->stream>>>(NSP_NUM_ARGS, bin_lo, bin_hi, queue, tmax, ctx->opt_unsorted ? 0 : 1, ctx->peer_out);
     ctx->prof_end();
     ctx->launches += 1;
     NSP_CUDA_TRY(ctx, cudaGetLastError());
@@ -533,6 +609,19 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
     c_rpt64 += row0;
     M = nrows;
     if (M == 0) return 0;
+    // Segment mode of the heavy class (spgemm_device.cuh stage_window_seg): B column-sorted, at most 4 windows,
+    // whole-matrix call (the cuts are indexed like A.col, which needs A.rpt[0] == 0).  Built BEFORE the plan's host
+    // sync, so that the side-stream launch of the long rows below does not wait behind it and still takes its SMs
+    // ahead of the main launch.
+    int seg_wshift = 16;
+    {
+        int ws_max = ctx->opt_num_window_shift > 0 ? (int)ctx->opt_num_window_shift : 19;
+        ws_max = ws_max < 16 ? 16 : (ws_max > 19 ? 19 : ws_max);
+        while (seg_wshift < ws_max && (1ll << seg_wshift) < (long long)N) ++seg_wshift;
+    }
+    const long long seg_nwin = ((long long)N + (1ll << seg_wshift) - 1) >> seg_wshift;
+    const bool use_seg = sp.b_sorted && seg_nwin <= 4 && row0 == 0 && nrows == sp.M && !ctx->opt_no_seg && sp.a_nnz > 0;
+    if (use_seg && build_entry_segments(ctx, a_col, sp.a_nnz, b_rpt, b_col, (int)seg_nwin, seg_wshift) != 0) return -1;
     if (plan_by_count(ctx, M, kNumShift, a_rpt, row0) != 0) return -1;
 
     // ---- class ladder (numeric shift 4: bin b holds 2^(3+b) < nnz <= 2^(4+b)) ----
@@ -592,21 +681,27 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
             return ctx->fail(-4, "nsp_spgemm_numeric: shared memory too small for the bitmap kernel");
         const size_t smem = fixed + (size_t)cap * (sizeof(real) + sizeof(int));
         const int grid = num_imin(num_rows_in(sp, bm_bin, kNumBins - 1), (long long)(sms - push_sms));
-        // [multi][peers][sorted]
-        void (*kerns[2][2][2])(const int *, const int *, const real *, const int *, const int *, const real *,
+        const long long a_entries = sp.a_nnz;
+        const int mode = !sp.b_sorted ? 0 : (use_seg ? 2 : 1);
+        // [multi][peers][mode]
+        void (*kerns[2][2][3])(const int *, const int *, const real *, const int *, const int *, const real *,
                                const long long *, int *, real *, const int *, int *, int, int, int, int, int, int, int,
-                               int, long long *, const PeerOut) = {
-            {{num_bitmap_kernel<real, 1024, false, false, false>, num_bitmap_kernel<real, 1024, true, false, false>},
-             {num_bitmap_kernel<real, 1024, false, true, false>, num_bitmap_kernel<real, 1024, true, true, false>}},
-            {{num_bitmap_kernel<real, 1024, false, false, true>, num_bitmap_kernel<real, 1024, true, false, true>},
-             {num_bitmap_kernel<real, 1024, false, true, true>, num_bitmap_kernel<real, 1024, true, true, true>}}};
+                               int, long long *, const int *, long long, const PeerOut) = {
+            {{num_bitmap_kernel<real, 1024, 0, false, false>, num_bitmap_kernel<real, 1024, 1, false, false>,
+              num_bitmap_kernel<real, 1024, 2, false, false>},
+             {num_bitmap_kernel<real, 1024, 0, true, false>, num_bitmap_kernel<real, 1024, 1, true, false>,
+              num_bitmap_kernel<real, 1024, 2, true, false>}},
+            {{num_bitmap_kernel<real, 1024, 0, false, true>, num_bitmap_kernel<real, 1024, 1, false, true>,
+              num_bitmap_kernel<real, 1024, 2, false, true>},
+             {num_bitmap_kernel<real, 1024, 0, true, true>, num_bitmap_kernel<real, 1024, 1, true, true>,
+              num_bitmap_kernel<real, 1024, 2, true, true>}}};
         // The long rows (few, each with millions of products: a tail of a handful of CTAs) go to a side stream
         // and start first; as their CTAs retire, the SMs pick up the CTAs of the main launch, whose dynamic row
         // queue balances whatever number of them is running.  Joined at the end of the phase.
         bool forked = false;
         for (int multi = 1; multi >= 0; --multi) {
             if (multi && !sp.has_multi_slab) continue;
-            auto kern = kerns[multi][peers ? 1 : 0][sp.b_sorted ? 1 : 0];
+            auto kern = kerns[multi][peers ? 1 : 0][mode];
             NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             cudaStream_t st = ctx->stream;
             if (multi && !ctx->opt_no_fork) {
@@ -619,7 +714,8 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
             num_prof_class(ctx, multi ? "num_bitmap_long" : "num_bitmap", bm_bin, kNumBins - 1);
             kern<<<grid, 1024, smem, st>>>(NSP_NUM_ARGS, bm_bin, kNumBins - 1, multi ? 5 : 4, N, wshift, cap,
                                            b_vec_end_of(ctx, b_col), (int)ctx->opt_debug,
-                                           ctx->opt_phase_timing ? ctx->phase_cycles() : nullptr, ctx->peer_out);
+                                           ctx->opt_phase_timing ? ctx->phase_cycles() : nullptr, use_seg ? ctx->d_seg : nullptr,
+                                           a_entries, ctx->peer_out);
             ctx->prof_end();
             ctx->prof_on_aux = false;
             ctx->launches += 1;

@@ -157,6 +157,56 @@ check_b_sorted_kernel(const int *__restrict__ b_rpt, const int *__restrict__ b_c
     if (tid == 0) unsorted[kScalarNnzB - kScalarUnsorted] = (unsigned long long)nnz;
 }
 
+// Window cuts of every B row an entry of A refers to, for the segment mode of the heavy numeric kernel
+// (spgemm_device.cuh stage_window_seg): seg[w * stride + j] = first product of entry j's B row at or beyond
+// column w << wshift, w = 0 .. nwin (w = 0: the row's start, w = nwin: its end).  One thread per entry, each cut
+// found by a binary search that starts at the previous one.  Needs column-sorted rows of B.
+__global__ void __launch_bounds__(256)
+entry_segments_kernel(const int *__restrict__ a_col, long long count, const int *__restrict__ b_rpt,
+                      const int *__restrict__ b_col, int nwin, int wshift, long long stride, int *__restrict__ seg)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const int ac = ld_stream(a_col + j);
+    int lo = ld_nc(b_rpt + ac);
+    const int ke = ld_nc(b_rpt + ac + 1);
+    seg[j] = lo;
+    for (int w = 1; w < nwin; ++w) {
+        const int key = (int)((unsigned)w << wshift);
+        int hi = ke;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (ld_nc(b_col + mid) < key) lo = mid + 1; else hi = mid;
+        }
+        seg[(long long)w * stride + j] = lo;
+    }
+    seg[(long long)nwin * stride + j] = ke;
+}
+
+// (nwin + 1) * count ints in the context's grow-only segment buffer; nullptr-safe for count == 0
+int build_entry_segments(nsp_context *ctx, const int *a_col, long long count, const int *b_rpt, const int *b_col,
+                         int nwin, int wshift)
+{
+    const size_t want = (size_t)(nwin + 1) * (size_t)(count > 0 ? count : 1);
+    if (want > ctx->seg_cap) {
+        NSP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->aux_stream) NSP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->aux_stream));
+        cudaFree(ctx->d_seg);
+        ctx->d_seg = nullptr;
+        ctx->seg_cap = 0;
+        const size_t cap = want + want / 8;
+        NSP_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_seg, sizeof(int) * cap));
+        ctx->seg_cap = cap;
+    }
+    if (count > 0) {
+        entry_segments_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(a_col, count, b_rpt, b_col, nwin, wshift,
+                                                                                      count, ctx->d_seg);
+        ctx->launches += 1;
+        NSP_CUDA_TRY(ctx, cudaGetLastError());
+    }
+    return 0;
+}
+
 // start[b] = number of rows in bins heavier than b; also clears cursors and queue heads.
 __global__ void bin_offsets_kernel(int *bins)
 {
@@ -365,6 +415,8 @@ int plan_by_intprod(nsp_context *ctx, int M, int K, int cap, const int *a_rpt, c
     sp.b_sorted = sp.h_scalars[kScalarUnsorted] == 0;
     sp.b_nnz = K > 0 && M > 0 ? sp.h_scalars[kScalarNnzB] : 0;
     sp.has_multi_slab = sp.h_scalars[kScalarMaxLen] > 1024;
+    sp.a_nnz = 0;
+    for (int b = 0; b < kNumBins; ++b) sp.a_nnz += (long long)sp.h_binsum[kSumLen + b];
     return 0;
 }
 

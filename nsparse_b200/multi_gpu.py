@@ -58,8 +58,35 @@ def partition_rows_by_cost(a_rpt, a_col, b_rpt, c_rpt, nparts: int, nnz_weight: 
     return cuts, int(ip_prefix[-1])
 
 
-def row_block(a: CSR, r0: int, r1: int) -> CSR:
-    """Rows [r0, r1) of A as a CSR of its own (row pointer rebased to 0)."""
+def partition_rows_by_ip_device(a, b, nparts: int):
+    """partition_rows_by_ip for matrices that live on the GPU (nsparse_b200.gen.DeviceCSR): the same cuts, computed
+    with torch on the device.  Returns (cuts, total_ip)."""
+    import torch
+
+    blen = (b.d_rpt[1:] - b.d_rpt[:-1]).long()
+    cs = torch.cumsum(blen[a.d_col.long()], 0)
+    prefix = torch.zeros(a.M + 1, dtype=torch.int64, device=cs.device)
+    rp = a.d_rpt.long()
+    nz = rp[1:] > 0
+    prefix[1:][nz] = cs[rp[1:][nz] - 1]
+    del cs
+    total = int(prefix[-1])
+    targets = torch.tensor([total * p // nparts for p in range(1, nparts)], dtype=torch.int64, device=prefix.device)
+    mid = torch.searchsorted(prefix, targets, right=False).tolist() if nparts > 1 else []
+    cuts = [0] + [int(x) for x in mid] + [a.M]
+    for i in range(1, len(cuts)):
+        cuts[i] = min(max(cuts[i], cuts[i - 1]), a.M)
+    return cuts, total
+
+
+def row_block(a, r0: int, r1: int):
+    """Rows [r0, r1) of A as a CSR of its own (row pointer rebased to 0); host CSR or DeviceCSR."""
+    if hasattr(a, "row_block"):
+        return a.row_block(r0, r1)
+    return _row_block_host(a, r0, r1)
+
+
+def _row_block_host(a: CSR, r0: int, r1: int) -> CSR:
     lo, hi = int(a.rpt[r0]), int(a.rpt[r1])
     return CSR(r1 - r0, a.N, (a.rpt[r0:r1 + 1] - a.rpt[r0]).astype(np.int32), a.col[lo:hi], a.val[lo:hi],
                f"{a.matrix_name}[{r0}:{r1}]")

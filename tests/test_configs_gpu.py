@@ -155,3 +155,66 @@ def test_numeric_by_row_ranges(ns, dtype):
         assert torch.equal(col[:done], col0[:done]) and torch.equal(val[:done], val0[:done])
         assert bool((col[done:] == -7).all())
     ctx.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_numeric_sort_false(ns, dtype):
+    """f1: option sort = 0 (SpGEMM_Hash_Numeric<sort = false>, HashSpGEMM_volta.hpp:508-605, 1018-1031): the columns
+    of a row may come out in any order, but as a SET with their values every row equals the oracle's."""
+    from nsparse_b200 import gen
+
+    a = gen.rmat_csr(12, 16, seed=9, dtype=dtype, values="small_int")
+    a.memcpy()
+    ctx = ns.Context(0)
+    ctx.set_option("sort", 0)
+    c = ns.spgemm_kernel_hash(a, a, ctx)
+    ctx.sync()
+    rpt, col, val = c.to_host()
+    want = oracle.spgemm(a.rpt, a.col, a.val, a.rpt, a.col, a.val, acc_double=True)
+    assert np.array_equal(rpt, want[0])
+    row = np.repeat(np.arange(a.M, dtype=np.int64), np.diff(rpt))
+    order = np.lexsort((col, row))
+    assert np.array_equal(col[order], want[1]) and np.array_equal(val[order], want[2])
+    assert not np.array_equal(col, want[1]), "sort = 0 had no effect (every row came out sorted)"
+    ctx.set_option("sort", 1)
+    c = ns.spgemm_kernel_hash(a, a, ctx)
+    ctx.sync()
+    assert np.array_equal(c.to_host()[1], want[1])
+    ctx.close()
+
+
+def test_device_generators_match_host(ns):
+    """The torch generators of the full-size C4 / C5 inputs: R-MAT edges and values are the host generator's, bit
+    for bit; the Erdos-Renyi and power-law rows are sorted, distinct and inside the matrix."""
+    from nsparse_b200 import gen
+
+    d = gen.rmat_csr_device(13, 16, seed=12345, dtype=np.float64, device=0)
+    h = gen.rmat_csr(13, 16, seed=12345, dtype=np.float64)
+    assert np.array_equal(d.d_rpt.cpu().numpy(), h.rpt) and np.array_equal(d.d_col.cpu().numpy(), h.col)
+    assert np.array_equal(d.d_val.cpu().numpy(), h.val)
+    e = gen.er_csr_device(20000, 1000, 4, device=0)
+    c = e.d_col.cpu().numpy().reshape(20000, 4)
+    assert (np.diff(c, axis=1) > 0).all() and c.min() >= 0 and c.max() < 1000
+    p = gen.powerlaw_csr_device(1 << 15, 64, 8192, device=0)
+    rpt, col = p.d_rpt.cpu().numpy(), p.d_col.cpu().numpy()
+    lens = np.diff(rpt)
+    assert lens.max() == 8192 and lens.min() >= 1 and 40 < lens.mean() < 90
+    inner = np.ones(len(col), bool)
+    inner[rpt[1:-1][lens[:-1] > 0] - 0] = False          # first entry of every row but the first
+    inner[0] = False
+    assert (np.diff(col.astype(np.int64))[inner[1:]] > 0).all() and col.min() >= 0 and col.max() < (1 << 15)
+    # the product of the device-generated pair against the oracle on a row sample
+    b = gen.er_csr_device(1 << 15, 1 << 15, 4, device=0)
+    ctx = ns.Context(0)
+    cprod = ns.spgemm_kernel_hash(p, b, ctx)
+    ctx.sync()
+    rows = np.arange(0, 1 << 15, 257)
+    sub, hb = p.rows_to_host(rows), b.to_host()
+    want = oracle.spgemm(sub.rpt, sub.col, sub.val, hb.rpt, hb.col, hb.val, acc_double=True, n_cols=hb.N)
+    g_rpt, g_col, g_val = cprod.to_host()
+    for k, r in enumerate(rows):
+        s, e2 = int(g_rpt[r]), int(g_rpt[r + 1])
+        ws, we = int(want[0][k]), int(want[0][k + 1])
+        assert e2 - s == we - ws and np.array_equal(g_col[s:e2], want[1][ws:we])
+        assert np.allclose(g_val[s:e2], want[2][ws:we], rtol=1e-12, atol=0)
+    ctx.close()
