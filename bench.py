@@ -489,6 +489,36 @@ def run_ours(args):
     ms_step = ms / args.steps
     gflops = 2.0 * ip / ms_step / 1e6
 
+    # -------- parity of a row sample against the CPU oracle + CPU baseline (rank 0) ----------------------------
+    cpu, parity = None, None
+    if rank == 0 and not args.no_cpu:
+        if wl["on_device"]:
+            # C4 / C5: a few hundred rows spread over the matrix (the full inputs never leave the GPU)
+            src = a_loc if world > 1 else a
+            rows = np.unique(np.linspace(0, src.M - 1, 257).astype(np.int64))
+            sub = src.rows_to_host(rows)
+            hb = b.to_host()
+            from oracle import oracle
+
+            tcpu = time.perf_counter()
+            oc = oracle.spgemm(sub.rpt, sub.col, sub.val, hb.rpt, hb.col, hb.val, acc_double=True, n_cols=hb.N)
+            tcpu = time.perf_counter() - tcpu
+            sub_ip = int(np.diff(hb.rpt).astype(np.int64)[sub.col].sum())
+            cpu = {"value": 2.0 * sub_ip / max(tcpu, 1e-9) / 1e9, "unit": "GFLOPS", "cores": oracle.num_threads(), "kind": "port",
+                   "sample": f"{len(rows)} rows spread over {'this rank\'s block of ' if world > 1 else ''}A times all of B: "
+                             f"{sub_ip} products, {tcpu:.2f} s"}
+            grows = rows + (cuts[rank] if world > 1 else 0)
+        else:
+            r, sub, oc = cpu_spgemm_sample(a, b, target_s=args.cpu_seconds, acc_double=True)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            grows = sub.rows
+        if c is not None:
+            parity = compare_rows(c, grows, oc, V)
+            parity["against"] = "CPU oracle (oracle/oracle.c, pinned to the reference's GPU output by tests/golden/spgemm_ref_*.npz)"
+        del oc, sub
+    if world > 1:
+        barrier()
+
     # -------- N > 1: the gathered C is the same everywhere and equals the single-GPU product -------------------
     gather = None
     if world > 1:
@@ -512,8 +542,7 @@ def run_ours(args):
                                   "exact, value sums within 1e-6, against rank 0's single-GPU product")
         # time without the gather: every rank computes its block only
         c = None
-        if peers is not None:
-            peers.col = peers.col            # (buffers stay allocated: the no-gather product goes to fresh memory)
+        # (the peer buffers stay allocated: the no-gather products go to fresh memory)
         torch.cuda.empty_cache()
         for _ in range(2):
             cl = ns.spgemm_kernel_hash(a_loc, b, ctx)
@@ -574,41 +603,7 @@ def run_ours(args):
                                "frac": whole / ms_step / 1e6 / max(world, 1) / peak},
                 "kernels": kernels}
 
-    # -------- parity of a row sample against the CPU oracle + CPU baseline (rank 0) ----------------------------
-    cpu, parity = None, None
-    if rank == 0 and not args.no_cpu:
-        if c is None:
-            c = step() if world == 1 else None
-        if wl["on_device"]:
-            # C4 / C5: a few hundred rows spread over the matrix (the full inputs never leave the GPU)
-            src = a_loc if world > 1 else a
-            rows = np.unique(np.linspace(0, src.M - 1, 257).astype(np.int64))
-            sub = src.rows_to_host(rows)
-            hb = b.to_host()
-            from oracle import oracle
-
-            tcpu = time.perf_counter()
-            oc = oracle.spgemm(sub.rpt, sub.col, sub.val, hb.rpt, hb.col, hb.val, acc_double=True, n_cols=hb.N)
-            tcpu = time.perf_counter() - tcpu
-            sub_ip = int(np.diff(hb.rpt).astype(np.int64)[sub.col].sum())
-            cpu = {"value": 2.0 * sub_ip / max(tcpu, 1e-9) / 1e9, "unit": "GFLOPS", "cores": oracle.num_threads(), "kind": "port",
-                   "sample": f"{len(rows)} rows spread over {'this rank\'s block of ' if world > 1 else ''}A times all of B: "
-                             f"{sub_ip} products, {tcpu:.2f} s"}
-            grows = rows + (cuts[rank] if world > 1 else 0)
-        else:
-            r, sub, oc = cpu_spgemm_sample(a, b, target_s=args.cpu_seconds, acc_double=True)
-            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-            grows = sub.rows
-        if world > 1 and c is None:
-            c = ns.spgemm_kernel_hash_mgpu(a_loc, b, cuts, n_rows, total_ip, ctx, peers=peers) if False else None
-        if c is not None:
-            parity = compare_rows(c, grows, oc, V)
-            parity["against"] = "CPU oracle (oracle/oracle.c, pinned to the reference's GPU output by tests/golden/spgemm_ref_*.npz)"
-        del oc, sub
-    if world > 1:
-        barrier()
     c = None
-
     # -------- end to end through the host-buffer C ABI ------------------------------------------------
     e2e = None
     if not args.no_e2e and args.config == "c2":

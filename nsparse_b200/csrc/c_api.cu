@@ -250,8 +250,27 @@ int nsp_spgemm_peers_status(nsp_context *ctx, int *h_error)
     if (ctl[2]) {
         *h_error = 1;
         NSP_CUDA_TRY(ctx, cudaMemset(ctx->d_push_ws + 2, 0, sizeof(int)));
+        // which tiles never filled up (diagnosis: a kernel that did not count its entries)
+        const nsp::PeerOut &po = ctx->last_push;
+        std::string detail;
+        if (po.ntiles > 0 && po.tile_cnt) {
+            std::vector<int> cnt((size_t)po.ntiles);
+            cudaMemcpy(cnt.data(), po.tile_cnt, sizeof(int) * (size_t)po.ntiles, cudaMemcpyDeviceToHost);
+            int shown = 0, bad = 0;
+            for (int t = 0; t < po.ntiles; ++t) {
+                const int want = nsp::tile_len(po, t);
+                if (cnt[t] != want) {
+                    ++bad;
+                    if (shown < 6) {
+                        detail += " tile " + std::to_string(t) + ": " + std::to_string(cnt[t]) + "/" + std::to_string(want);
+                        ++shown;
+                    }
+                }
+            }
+            detail = "; " + std::to_string(bad) + " of " + std::to_string(po.ntiles) + " tiles incomplete:" + detail;
+        }
         return ctx->fail(NSP_ERR_CUDA, "multi-GPU allgatherv: the pusher kernel gave up waiting for a tile of C (" +
-                                           std::to_string(ctl[0]) + " tiles were published)");
+                                           std::to_string(ctl[0]) + " tiles were published" + detail + ")");
     }
     return 0;
 }

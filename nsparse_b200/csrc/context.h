@@ -98,6 +98,7 @@ struct nsp_context {
 
     nsp_spgemm_state sp;
     nsp::PeerOut peer_out;   // nsp_spgemm_set_peers
+    nsp::PeerOut last_push;  // the tile hand-off of the last product (diagnostics of nsp_spgemm_peers_status)
     // tile hand-off + pusher kernel of the multi-GPU allgatherv (peer_push.cu)
     cudaStream_t push_stream = nullptr;
     cudaEvent_t ev_push_fork = nullptr, ev_push_join = nullptr;
@@ -105,6 +106,7 @@ struct nsp_context {
     size_t push_cap = 0;
     bool push_active = false;
     int push_ctas = 0;
+    bool peers_preloaded[2] = {false, false};   // numeric kernels loaded ahead of the pusher (fp32, fp64)
     long long opt_push_sms = 0;          // CTAs (= SMs) of the pusher kernel (0: default 16)
     nsp_host_result host;
 

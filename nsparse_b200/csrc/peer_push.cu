@@ -177,6 +177,7 @@ int peer_push_begin(nsp_context *ctx, const int *c_col_full, const void *c_val_f
     NSP_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_push_join, ctx->push_stream));
     ctx->push_active = true;
     ctx->push_ctas = ctas;
+    ctx->last_push = po;
     return 0;
 }
 

@@ -590,6 +590,30 @@ static int launch_num_hash(nsp_context *ctx, const char *name, int grid, size_t 
     return 0;
 }
 
+// CUDA loads kernels lazily, on their first launch, and the load may need a context-wide synchronisation: it then
+// waits for every running kernel -- also for the persistent pusher kernel of the multi-GPU path, which itself waits
+// for the kernels being loaded.  Every function the numeric phase can launch while the pusher runs is therefore
+// loaded BEFORE the pusher starts (cudaFuncGetAttributes forces the load); once per context and precision.
+template <typename real>
+static int preload_numeric_kernels(nsp_context *ctx)
+{
+    const int which = sizeof(real) == 8 ? 1 : 0;
+    if (ctx->peers_preloaded[which]) return 0;
+    cudaFuncAttributes at;
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_pwarp_kernel<real>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_hash_kernel<real, 32, 256>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_hash_kernel<real, 256, 256>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_hash_kernel<real, 1024, 1024>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 0, true, false>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 1, true, false>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 2, true, false>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 0, true, true>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 1, true, true>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 2, true, true>));
+    ctx->peers_preloaded[which] = true;
+    return 0;
+}
+
 template <typename real>
 int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, const int *a_col,
                    const real *a_val, const int *b_rpt, const int *b_col, const real *b_val,
@@ -671,6 +695,7 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
     long long nnz_block = 0;
     for (int b = 0; b < kNumBins; ++b) nnz_block += (long long)sp.h_binsum[kSumCnt + b];
     // multi-GPU: the pusher kernel takes its SMs first (peer_push.cu); the computing kernels only count tiles
+    if (peers && preload_numeric_kernels<real>(ctx) != 0) return -1;
     if (peers && peer_push_begin(ctx, c_col - ctx->peer_out.off, c_val - ctx->peer_out.off, (int)sizeof(real), nnz_block) != 0)
         return -1;
     const int push_sms = ctx->push_active ? ctx->push_ctas : 0;

@@ -380,3 +380,39 @@ def test_host_drain_fold(ns, ctx):
             moved += len(chunk)
     assert nnz.value == int(want[0][-1]) and nbytes.value == moved and csum.value == fold
     ctx.check(ctx.lib.nsp_spgemm_host_release(ctx.handle))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("offset", [0, 12345])
+def test_tile_pusher_on_one_gpu(ns, ctx, dtype, offset):
+    """The multi-GPU allgatherv path (tile counters in every numeric kernel + the TMA pusher kernel, csrc/peer_push.cu)
+    with the 'peer' being a second buffer on the SAME GPU: after the product the peer copy must equal C entry for
+    entry at the block's displacement, and nothing outside the block may have been touched."""
+    import ctypes as C
+
+    import torch
+
+    from nsparse_b200 import gen
+
+    a = gen.rmat_csr(13, 16, seed=4, dtype=dtype, values="small_int")
+    a.memcpy()
+    d_rpt64, nnz, _ = ns.spgemm_symbolic(a, a, ctx)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    total = offset + nnz + 999
+    col = torch.full((total,), -7, dtype=torch.int32, device="cuda")
+    val = torch.full((total,), -7, dtype=tdt, device="cuda")
+    pcol = torch.full((total,), -7, dtype=torch.int32, device="cuda")
+    pval = torch.full((total,), -7, dtype=tdt, device="cuda")
+    ctx.check(ctx.lib.nsp_spgemm_set_peers(ctx.handle, 1, (C.c_void_p * 1)(pcol.data_ptr()), (C.c_void_p * 1)(pval.data_ptr()), offset))
+    try:
+        ns.spgemm_numeric(a, a, d_rpt64, nnz, ctx, out=(col[offset:], val[offset:]))
+    finally:
+        ctx.check(ctx.lib.nsp_spgemm_set_peers(ctx.handle, 0, None, None, 0))
+    err = C.c_int(0)
+    ctx.check(ctx.lib.nsp_spgemm_peers_status(ctx.handle, C.byref(err)))
+    assert err.value == 0
+    want = oracle.spgemm(a.rpt, a.col, a.val, a.rpt, a.col, a.val, acc_double=True)
+    assert np.array_equal(col[offset:offset + nnz].cpu().numpy(), want[1])
+    assert np.array_equal(val[offset:offset + nnz].cpu().numpy(), want[2])
+    assert torch.equal(pcol, col) and torch.equal(pval, val)
+    assert int((pcol[:offset] != -7).sum()) == 0 and int((pcol[offset + nnz:] != -7).sum()) == 0
