@@ -32,10 +32,10 @@ constexpr unsigned kHashMul = 0x9E3779B1u;
 // kernels only COUNT: whoever has written entries [s, e) of the block adds the overlap to the counter of every
 // tile it touches (tiles_done below), and the thread that completes a tile appends it to a ready queue.  A
 // persistent pusher kernel on a few SMs of its own (push_tiles_kernel) takes the ready tiles in completion
-// order and stores them into every peer through the TMA (cp.async.bulk shared -> peer global), so the NVLink
+// order and moves them into every peer with the TMA alone (cp.async.bulk global -> shared -> peer global), so the NVLink
 // transfer runs next to the compute instead of inside the computing CTAs.  n == 0: single GPU.
 constexpr int kMaxPeerOut = 7;
-constexpr int kTileLog = 13;               // 8192 entries: 32 KiB of C.col + 32 / 64 KiB of C.val per tile
+constexpr int kTileLog = 12;               // 4096 entries: 16 KiB of C.col + 16 / 32 KiB of C.val per tile
 struct PeerOut {
     int n = 0;
     long long off = 0;

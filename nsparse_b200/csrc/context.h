@@ -175,8 +175,13 @@ template <typename real>
 int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, const int *a_col,
                    const real *a_val, const int *b_rpt, const int *b_col, const real *b_val,
                    const long long *c_rpt64, int *c_col, real *c_val, int row0 = 0, int nrows = -1);
+// everything the numeric phase with peers would allocate or load lazily, done ahead (single-process multi-GPU:
+// see peer_push_reserve)
+template <typename real>
+int spgemm_numeric_reserve(nsp_context *ctx, int N, long long a_nnz, long long nnz_block);
 int rpt64_to_rpt32(nsp_context *ctx, int M, const long long *rpt64, long long nnz, int *rpt32);
 // peer_push.cu
+int peer_push_reserve(nsp_context *ctx, long long ntiles);
 int peer_push_begin(nsp_context *ctx, const int *c_col_full, const void *c_val_full, int val_bytes, long long nnz_block);
 int peer_push_end(nsp_context *ctx);
 

@@ -31,7 +31,7 @@ struct nsp_mgpu {
         long long *rpt_local = nullptr;
         size_t a_rows_cap = 0, a_nnz_cap = 0, b_rows_cap = 0, b_nnz_cap = 0;
         int val_bytes = 0;
-        long long nnz = 0, ip = 0;
+        long long nnz = 0, ip = 0, a_nnz = 0;
         int rc = 0;
         double ms_symbolic = 0, ms_numeric = 0;
     };
@@ -174,6 +174,7 @@ int mgpu_symbolic(nsp_mgpu *mg, int M, int K, int N, const int *a_rpt, const int
         MG_TRY(ctx, cudaMemcpy(d.b_col, b_col, sizeof(int) * (size_t)b_nnz, cudaMemcpyHostToDevice));
         MG_TRY(ctx, cudaMemcpy(d.b_val, b_val, sizeof(real) * (size_t)b_nnz, cudaMemcpyHostToDevice));
         d.nnz = d.ip = 0;
+        d.a_nnz = nnz;
         const int rc = nsp::spgemm_symbolic(ctx, rows, K, N, d.a_rpt, d.a_col, d.b_rpt, d.b_col, d.rpt_local, &d.nnz, &d.ip);
         d.ms_symbolic = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         return rc;
@@ -194,6 +195,13 @@ int mgpu_numeric(nsp_mgpu *mg, long long *const *c_rpt64, int *const *c_col, rea
     if (!mg->symbolic_done || mg->val_bytes != (int)sizeof(real))
         return mg->fail(NSP_ERR_ARG, "nsp_mgpu_spgemm_numeric: call nsp_mgpu_spgemm_symbolic of the same precision first");
     const long long tot = mg->disp[mg->n];
+    // Phase A on every GPU, THEN phase B: whatever allocates device memory or loads code happens before the first
+    // pusher kernel starts spinning anywhere -- cudaMalloc on one GPU of a process with peer access enabled
+    // synchronises with its peers, i.e. it would wait for their pushers, which wait for kernels queued behind it.
+    for_each_gpu(mg, [&](int g) -> int {
+        return nsp::spgemm_numeric_reserve<real>(mg->ctx[g], mg->N, mg->d[g].a_nnz, mg->d[g].nnz);
+    });
+    if (int rc = first_error(mg, "numeric phase (reserve)")) return rc;
     for_each_gpu(mg, [&](int g) -> int {
         nsp_context *ctx = mg->ctx[g];
         nsp_mgpu::Dev &d = mg->d[g];

@@ -1,23 +1,51 @@
 // nsparse-b200: the pusher of the multi-GPU allgatherv (see PeerOut in common.cuh).
 //
 // A persistent kernel on a few SMs of its own, launched on a side stream BEFORE the numeric kernels of a
-// product.  Its CTAs draw tickets; ticket k waits until the k-th completed tile of this rank's block of C
-// has been published by the numeric kernels (tiles_done), stages the tile's C.col and C.val in shared memory
-// with 128-bit loads (they were written moments ago: L2 hits) and hands the two buffers to the TMA:
-// one cp.async.bulk shared -> global per peer and array, i.e. 2 * npeers bulk stores of 32 / 64 KiB that
-// the copy engine of the SM carries over NVLink while the CTA already waits for and loads its next tile
-// (two stages; a stage is reused when cp.async.bulk.wait_group.read says its bulk stores have left shared
-// memory).  The computing SMs never execute a remote store.
+// product.  One warp per CTA, and of that warp one thread: it drives the TMA.  The thread draws tickets; ticket
+// k is the k-th tile of this rank's block of C that the numeric kernels complete (tiles_done).  As soon as a
+// ticket's tile is published the thread issues two bulk loads global -> shared (cp.async.bulk ... mbarrier::
+// complete_tx: C.col and C.val of the tile, written moments ago by the computing SMs: L2 hits) into the next
+// free stage of a ring in shared memory; when a stage's mbarrier says the bytes have landed it issues one bulk
+// store shared -> global per peer and array (2 * npeers stores of 16 / 32 KiB over NVLink) and commits them as
+// a bulk group; a stage is reused when cp.async.bulk.wait_group.read says the stores have read it.  With a ring
+// of kStages the SM has kStages tiles in flight in each direction and no thread ever touches the data: the
+// first version (threads load, then hand to the TMA, two stages) was latency bound at ~15 GB/s per SM
+// (profiles/r2_bench_g2_pusher_v1_*.json).  The computing SMs never execute a remote store.
 //
-// Tiles are aligned in the full arrays (all bases are 256-byte aligned allocations), so every tile but the
-// first and the last of the block is one aligned bulk copy; the up to three entries that a ragged block end
-// leaves outside 16-byte granules are stored with plain 4 / 8-byte stores.
+// Tiles are aligned in the full arrays (all bases are 256-byte aligned allocations), so every tile but the first
+// and the last of the block is two aligned bulk copies; the at most six entries that a ragged block end leaves
+// outside 16-byte granules are copied by the thread itself.
 #include "context.h"
 
 namespace nsp {
 
+constexpr int kPushStagesBytes = 192 * 1024;      // ring of the pusher CTA (one CTA per SM)
+
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_load(void *sdst, const void *gsrc, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigned bytes)
 {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
@@ -25,7 +53,7 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigne
 }
 
 template <int VB>   // bytes per value
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(32, 1)
 push_tiles_kernel(const int *__restrict__ c_col, const unsigned char *__restrict__ c_val, long long spin_limit,
                   const __grid_constant__ PeerOut peer)
 {
@@ -33,86 +61,120 @@ push_tiles_kernel(const int *__restrict__ c_col, const unsigned char *__restrict
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int T = 1 << kTileLog;
     constexpr int kStageBytes = T * (4 + VB);
-    __shared__ int s_tile;
-    const int t = threadIdx.x;
-    int stage = 0;
+    constexpr int kStages = kPushStagesBytes / kStageBytes;
+    static_assert(kStages >= 2 && kStages <= 8, "ring depth");
+    __shared__ __align__(8) unsigned long long s_full[kStages];
+    if (threadIdx.x != 0) return;
+    for (int s = 0; s < kStages; ++s) mbar_init(&s_full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+
+    // per stage: what was loaded (entries [ca, cb) of col as granules, [va, vb) of val)
+    long long st_ca[kStages], st_va[kStages];
+    int st_ncg[kStages], st_nvg[kStages];
+    unsigned phase = 0;                          // bit s: parity the next wait on stage s expects
+    int loaded = 0, stored = 0;                  // tiles whose loads were issued / whose stores were issued
+    int ticket = -1;                             // a ticket drawn but not yet published by the producers
+    bool drained = false;                        // no tickets left
+    long long t_wait = 0;
+    constexpr int VG = 16 / VB;
     while (true) {
-        if (t == 0) {
-            int tile = -2;
-            const int ticket = atomicAdd(peer.q_ctl + 1, 1);
-            if (ticket < peer.ntiles) {
-                const long long t0 = clock64();
-                while (true) {
-                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(tile) : "l"(peer.queue + ticket) : "memory");
-                    if (tile >= 0) break;
-                    if (clock64() - t0 > spin_limit) {          // a producer never finished: report, do not hang
-                        atomicExch(peer.q_ctl + 2, 1);
-                        tile = -2;
-                        break;
+        bool progress = false;
+        // ---- issue loads: next ticket into the next free stage ----
+        if (!drained && loaded - stored < kStages) {
+            if (ticket < 0) {
+                ticket = atomicAdd(peer.q_ctl + 1, 1);
+                if (ticket >= peer.ntiles) {
+                    drained = true;
+                    ticket = -1;
+                } else {
+                    t_wait = clock64();
+                }
+            }
+            if (ticket >= 0) {
+                int tile;
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(tile) : "l"(peer.queue + ticket) : "memory");
+                if (tile >= 0) {
+                    const int s = loaded % kStages;
+                    // the stage was handed to the bulk stores kStages tiles ago: that group must have read it, i.e. at
+                    // most kStages - 1 - (loaded - stored) of the groups committed since may still be reading
+                    switch (kStages - 1 - (loaded - stored)) {
+                        case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+                        case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+                        case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+                        case 3: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+                        case 4: asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory"); break;
+                        case 5: asm volatile("cp.async.bulk.wait_group.read 5;" ::: "memory"); break;
+                        case 6: asm volatile("cp.async.bulk.wait_group.read 6;" ::: "memory"); break;
+                        default: asm volatile("cp.async.bulk.wait_group.read 7;" ::: "memory"); break;
                     }
-                    __nanosleep(256);
-                }
-            }
-            s_tile = tile;
-            // the stage about to be overwritten was handed to the TMA two tiles ago
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        }
-        __syncthreads();
-        const int tile = s_tile;
-        if (tile < 0) break;
-        // entries [a, b) of the full arrays
-        const long long lo = (peer.tile0 + tile) << kTileLog;
-        const long long a = lo > peer.off ? lo : peer.off;
-        const long long b = (lo + T) < (peer.off + peer.nnz) ? (lo + T) : (peer.off + peer.nnz);
-        unsigned char *s_col = smem + (size_t)stage * kStageBytes;
-        unsigned char *s_val = s_col + (size_t)T * 4;
-        // 16-byte granules of the tile that lie completely inside [a, b), per array
-        const long long ca = (a + 3) & ~3ll, cb = b & ~3ll;                                  // col: 4 entries per granule
-        constexpr int VG = 16 / VB;
-        const long long va = (a + VG - 1) & ~(long long)(VG - 1), vb = b & ~(long long)(VG - 1);
-        const int ncg = cb > ca ? (int)((cb - ca) >> 2) : 0;
-        const int nvg = vb > va ? (int)((vb - va) / VG) : 0;
-        {
-            const uint4 *g = reinterpret_cast<const uint4 *>(c_col + ca);
-            uint4 *s = reinterpret_cast<uint4 *>(s_col);
-            for (int i = t; i < ncg; i += 256) s[i] = __ldcg(g + i);
-            const uint4 *gv = reinterpret_cast<const uint4 *>(c_val + (size_t)va * VB);
-            uint4 *sv = reinterpret_cast<uint4 *>(s_val);
-            for (int i = t; i < nvg; i += 256) sv[i] = __ldcg(gv + i);
-        }
-        // ragged ends (first / last tile of the block only): plain stores straight to the peers
-        if (ncg == 0 || ca != a || cb != b || va != a || vb != b) {
-            for (long long k = a + t; k < b; k += 256) {
-                const bool col_edge = ncg == 0 || k < ca || k >= cb;
-                const bool val_edge = nvg == 0 || k < va || k >= vb;
-                if (col_edge) {
-                    const int c = __ldcg(c_col + k);
-                    for (int p = 0; p < peer.n; ++p) peer.col[p][k] = c;
-                }
-                if (val_edge) {
-                    if (VB == 4) {
-                        const unsigned v = __ldcg(reinterpret_cast<const unsigned *>(c_val) + k);
-                        for (int p = 0; p < peer.n; ++p) static_cast<unsigned *>(peer.val[p])[k] = v;
-                    } else {
-                        const unsigned long long v = __ldcg(reinterpret_cast<const unsigned long long *>(c_val) + k);
-                        for (int p = 0; p < peer.n; ++p) static_cast<unsigned long long *>(peer.val[p])[k] = v;
+                    const long long lo = (peer.tile0 + tile) << kTileLog;
+                    const long long a = lo > peer.off ? lo : peer.off;
+                    const long long b = (lo + T) < (peer.off + peer.nnz) ? (lo + T) : (peer.off + peer.nnz);
+                    const long long ca = (a + 3) & ~3ll, cb = b & ~3ll;
+                    const long long va = (a + VG - 1) & ~(long long)(VG - 1), vb = b & ~(long long)(VG - 1);
+                    const int ncg = cb > ca ? (int)((cb - ca) >> 2) : 0;
+                    const int nvg = vb > va ? (int)((vb - va) / VG) : 0;
+                    st_ca[s] = ca;
+                    st_va[s] = va;
+                    st_ncg[s] = ncg;
+                    st_nvg[s] = nvg;
+                    // the tile was written through the generic proxy by other SMs (made visible by the acquire above);
+                    // the TMA reads through the async proxy
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
+                    unsigned char *s_col = smem + (size_t)s * kStageBytes;
+                    unsigned char *s_val = s_col + (size_t)T * 4;
+                    mbar_expect_tx(&s_full[s], (unsigned)(ncg + nvg) * 16u);
+                    if (ncg) bulk_load(s_col, c_col + ca, (unsigned)ncg * 16u, &s_full[s]);
+                    if (nvg) bulk_load(s_val, c_val + (size_t)va * VB, (unsigned)nvg * 16u, &s_full[s]);
+                    // ragged ends (first / last tile of the block): at most six entries, copied right here
+                    if (ca != a || cb != b || va != a || vb != b || ncg == 0 || nvg == 0) {
+                        for (long long k = a; k < b; ++k) {
+                            if (ncg == 0 || k < ca || k >= cb) {
+                                const int c = __ldcg(c_col + k);
+                                for (int p = 0; p < peer.n; ++p) peer.col[p][k] = c;
+                            }
+                            if (nvg == 0 || k < va || k >= vb) {
+                                if (VB == 4) {
+                                    const unsigned v = __ldcg(reinterpret_cast<const unsigned *>(c_val) + k);
+                                    for (int p = 0; p < peer.n; ++p) static_cast<unsigned *>(peer.val[p])[k] = v;
+                                } else {
+                                    const unsigned long long v = __ldcg(reinterpret_cast<const unsigned long long *>(c_val) + k);
+                                    for (int p = 0; p < peer.n; ++p) static_cast<unsigned long long *>(peer.val[p])[k] = v;
+                                }
+                            }
+                        }
                     }
+                    ++loaded;
+                    ticket = -1;
+                    progress = true;
+                } else if (clock64() - t_wait > spin_limit) {     // a producer never finished: report, do not hang
+                    atomicExch(peer.q_ctl + 2, 1);
+                    drained = true;
+                    ticket = -1;
                 }
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async-proxy reads
-        __syncthreads();
-        if (t == 0) {
-            for (int p = 0; p < peer.n; ++p) {
-                if (ncg) bulk_store(peer.col[p] + ca, s_col, (unsigned)ncg * 16u);
-                if (nvg) bulk_store(static_cast<unsigned char *>(peer.val[p]) + (size_t)va * VB, s_val, (unsigned)nvg * 16u);
+        // ---- issue stores: the oldest loaded stage, once its bytes have landed ----
+        if (stored < loaded) {
+            const int s = stored % kStages;
+            if (mbar_try_wait(&s_full[s], (phase >> s) & 1u)) {
+                phase ^= 1u << s;
+                unsigned char *s_col = smem + (size_t)s * kStageBytes;
+                unsigned char *s_val = s_col + (size_t)T * 4;
+                for (int p = 0; p < peer.n; ++p) {
+                    if (st_ncg[s]) bulk_store(peer.col[p] + st_ca[s], s_col, (unsigned)st_ncg[s] * 16u);
+                    if (st_nvg[s]) bulk_store(static_cast<unsigned char *>(peer.val[p]) + (size_t)st_va[s] * VB, s_val, (unsigned)st_nvg[s] * 16u);
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                ++stored;
+                progress = true;
             }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        stage ^= 1;
+        if (drained && stored == loaded) break;
+        if (!progress) __nanosleep(128);
     }
     // all bulk stores of this CTA complete (not just read) before the kernel ends
-    if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 __global__ void push_init_kernel(int *tile_cnt, int *queue, int *q_ctl, int ntiles)
@@ -125,23 +187,19 @@ __global__ void push_init_kernel(int *tile_cnt, int *queue, int *q_ctl, int ntil
     if (i < 2) q_ctl[i] = 0;       // tail, head; the error flag [2] is sticky until read
 }
 
-// workspace of the tile hand-off (grow-only), PeerOut's tile fields, and the pusher launch on the push stream.
-// Called by spgemm_numeric right before its kernels when peers are set.
-int peer_push_begin(nsp_context *ctx, const int *c_col_full, const void *c_val_full, int val_bytes, long long nnz_block)
+// Everything of the hand-off that ALLOCATES (workspace for `ntiles` tiles, side stream, events) or loads code:
+// peer_push_begin calls it, and the single-process multi-GPU entry calls it on every GPU BEFORE any pusher starts
+// (cudaMalloc on one GPU of a process with peer access enabled synchronises with the peers, i.e. would wait for
+// their spinning pushers).
+int peer_push_reserve(nsp_context *ctx, long long ntiles)
 {
-    PeerOut &po = ctx->peer_out;
-    po.nnz = nnz_block;
-    po.tile0 = po.off >> kTileLog;
-    po.ntiles = nnz_block > 0 ? (int)(((po.off + nnz_block - 1) >> kTileLog) - po.tile0 + 1) : 0;
-    ctx->push_active = false;
-    if (po.n <= 0 || po.ntiles == 0) return 0;
-    if ((size_t)po.ntiles > ctx->push_cap) {
+    if ((size_t)ntiles > ctx->push_cap) {
         NSP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         if (ctx->push_stream) NSP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->push_stream));
         cudaFree(ctx->d_push_ws);
         ctx->d_push_ws = nullptr;
         ctx->push_cap = 0;
-        const size_t cap = (size_t)po.ntiles + (size_t)po.ntiles / 8 + 64;
+        const size_t cap = (size_t)ntiles + (size_t)ntiles / 8 + 64;
         NSP_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_push_ws, sizeof(int) * (2 * cap + 8)));
         NSP_CUDA_TRY(ctx, cudaMemset(ctx->d_push_ws, 0, sizeof(int) * (2 * cap + 8)));
         ctx->push_cap = cap;
@@ -150,7 +208,27 @@ int peer_push_begin(nsp_context *ctx, const int *c_col_full, const void *c_val_f
         NSP_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->push_stream, cudaStreamNonBlocking));
         NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_push_fork, cudaEventDisableTiming));
         NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_push_join, cudaEventDisableTiming));
+        cudaFuncAttributes at;
+        NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, push_tiles_kernel<4>));
+        NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, push_tiles_kernel<8>));
+        NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, push_init_kernel));
+        NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(push_tiles_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPushStagesBytes));
+        NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(push_tiles_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPushStagesBytes));
     }
+    return 0;
+}
+
+// PeerOut's tile fields and the pusher launch on the push stream.  Called by spgemm_numeric right before its
+// kernels when peers are set.
+int peer_push_begin(nsp_context *ctx, const int *c_col_full, const void *c_val_full, int val_bytes, long long nnz_block)
+{
+    PeerOut &po = ctx->peer_out;
+    po.nnz = nnz_block;
+    po.tile0 = po.off >> kTileLog;
+    po.ntiles = nnz_block > 0 ? (int)(((po.off + nnz_block - 1) >> kTileLog) - po.tile0 + 1) : 0;
+    ctx->push_active = false;
+    if (po.n <= 0 || po.ntiles == 0) return 0;
+    if (peer_push_reserve(ctx, po.ntiles) != 0) return -1;
     po.q_ctl = ctx->d_push_ws;
     po.tile_cnt = ctx->d_push_ws + 8;
     po.queue = po.tile_cnt + ctx->push_cap;
@@ -162,16 +240,12 @@ int peer_push_begin(nsp_context *ctx, const int *c_col_full, const void *c_val_f
     int ctas = ctx->opt_push_sms > 0 ? (int)ctx->opt_push_sms : 16;
     if (ctas > ctx->sm_count / 2) ctas = ctx->sm_count / 2;
     if (ctas > po.ntiles) ctas = po.ntiles;
-    const size_t smem = (size_t)2 * (1u << kTileLog) * (4 + val_bytes);
     const long long spin_limit = 20ll * 1000 * 1000 * 1000;      // ~10 s of SM clocks: a hang guard, not a schedule
     const unsigned char *cv = static_cast<const unsigned char *>(c_val_full);
-    if (val_bytes == 4) {
-        NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(push_tiles_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        push_tiles_kernel<4><<<ctas, 256, smem, ctx->push_stream>>>(c_col_full, cv, spin_limit, po);
-    } else {
-        NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(push_tiles_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        push_tiles_kernel<8><<<ctas, 256, smem, ctx->push_stream>>>(c_col_full, cv, spin_limit, po);
-    }
+    if (val_bytes == 4)
+        push_tiles_kernel<4><<<ctas, 32, kPushStagesBytes, ctx->push_stream>>>(c_col_full, cv, spin_limit, po);
+    else
+        push_tiles_kernel<8><<<ctas, 32, kPushStagesBytes, ctx->push_stream>>>(c_col_full, cv, spin_limit, po);
     ctx->launches += 1;
     NSP_CUDA_TRY(ctx, cudaGetLastError());
     NSP_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_push_join, ctx->push_stream));

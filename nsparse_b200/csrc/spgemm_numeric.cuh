@@ -615,6 +615,19 @@ static int preload_numeric_kernels(nsp_context *ctx)
 }
 
 template <typename real>
+int spgemm_numeric_reserve(nsp_context *ctx, int N, long long a_nnz, long long nnz_block)
+{
+    if (preload_numeric_kernels<real>(ctx) != 0) return -1;
+    int ws_max = ctx->opt_num_window_shift > 0 ? (int)ctx->opt_num_window_shift : 19;
+    ws_max = ws_max < 16 ? 16 : (ws_max > 19 ? 19 : ws_max);
+    int wshift = 16;
+    while (wshift < ws_max && (1ll << wshift) < (long long)N) ++wshift;
+    const long long nwin = ((long long)N + (1ll << wshift) - 1) >> wshift;
+    if (nwin <= 4 && !ctx->opt_no_seg && reserve_entry_segments(ctx, a_nnz, (int)nwin) != 0) return -1;
+    return peer_push_reserve(ctx, (nnz_block >> kTileLog) + 2);
+}
+
+template <typename real>
 int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, const int *a_col,
                    const real *a_val, const int *b_rpt, const int *b_col, const real *b_val,
                    const long long *c_rpt64, int *c_col, real *c_val, int row0, int nrows)

@@ -183,9 +183,8 @@ entry_segments_kernel(const int *__restrict__ a_col, long long count, const int 
     seg[(long long)nwin * stride + j] = ke;
 }
 
-// (nwin + 1) * count ints in the context's grow-only segment buffer; nullptr-safe for count == 0
-int build_entry_segments(nsp_context *ctx, const int *a_col, long long count, const int *b_rpt, const int *b_col,
-                         int nwin, int wshift)
+// (nwin + 1) * count ints in the context's grow-only segment buffer
+int reserve_entry_segments(nsp_context *ctx, long long count, int nwin)
 {
     const size_t want = (size_t)(nwin + 1) * (size_t)(count > 0 ? count : 1);
     if (want > ctx->seg_cap) {
@@ -198,6 +197,13 @@ int build_entry_segments(nsp_context *ctx, const int *a_col, long long count, co
         NSP_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_seg, sizeof(int) * cap));
         ctx->seg_cap = cap;
     }
+    return 0;
+}
+
+int build_entry_segments(nsp_context *ctx, const int *a_col, long long count, const int *b_rpt, const int *b_col,
+                         int nwin, int wshift)
+{
+    if (reserve_entry_segments(ctx, count, nwin) != 0) return -1;
     if (count > 0) {
         entry_segments_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(a_col, count, b_rpt, b_col, nwin, wshift,
                                                                                       count, ctx->d_seg);

@@ -46,6 +46,7 @@ int plan_by_intprod(nsp_context *ctx, int M, int K, int cap, const int *a_rpt, c
                     const int *b_rpt, const int *b_col);
 int plan_by_count(nsp_context *ctx, int M, int shift, const int *a_rpt, int row0 = 0);
 int scan_row_counts(nsp_context *ctx, int M, long long *rpt64);
+int reserve_entry_segments(nsp_context *ctx, long long count, int nwin);
 int build_entry_segments(nsp_context *ctx, const int *a_col, long long count, const int *b_rpt, const int *b_col,
                          int nwin, int wshift);
 
