@@ -12,7 +12,7 @@ OBJ       := build/obj
 LIBDIR    := nsparse_b200/lib
 BIN       := bin
 
-CORE_CU   := context peer_push spgemm_plan spgemm_symbolic spgemm_numeric_s spgemm_numeric_d c_api mgpu_api amb_convert amb_spmv amb_api
+CORE_CU   := context peer_push peer_dma spgemm_plan spgemm_symbolic spgemm_numeric_s spgemm_numeric_d c_api mgpu_api amb_convert amb_spmv amb_api
 CORE_OBJ  := $(addprefix $(OBJ)/,$(addsuffix .o,$(CORE_CU))) $(OBJ)/gen.o $(OBJ)/mtx_reader.o
 
 .PHONY: all lib compat drivers clean oracle

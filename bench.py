@@ -395,6 +395,8 @@ def run_ours(args):
     ctx = ns.Context(local)
     if args.push_sms:
         ctx.set_option("push_sms", args.push_sms)
+    if args.gather_tma:
+        ctx.set_option("gather_tma", 1)
     if not wl["on_device"]:
         b.memcpy(local)                    # B (replicated); A is B for C2
     torch.cuda.synchronize()
@@ -630,8 +632,11 @@ def run_ours(args):
     if rank == 0:
         gather_txt = ("NCCL broadcasts" if args.nccl_gather else
                       "a copy kernel stores the finished block into all peers over NVLink (nsp_push_to_peers)" if args.gather == "push" else
-                      "overlapped: the numeric kernels count finished tiles of C and a pusher kernel on a few SMs of its own stores "
-                      "them into all peers through the TMA while the rest computes (nsp_spgemm_set_peers)" if args.gather == "fused" else
+                      "overlapped, TMA pusher: the numeric kernels count finished tiles of C and a pusher kernel on a few SMs of its "
+                      "own moves them into all peers with cp.async.bulk while the rest computes" if (args.gather == "fused" and args.gather_tma) else
+                      "overlapped, copy engines: the heavy rows are computed tile by tile, the numeric kernels count finished entries "
+                      "per tile, and the calling host thread hands every finished tile to cudaMemcpyAsync for each peer while the "
+                      "rest is computed (nsp_spgemm_set_peers)" if args.gather == "fused" else
                       f"pipelined: the block is computed in {args.pieces} pieces, the copy engines carry every finished piece")
         line = {
             "metric": "SpGEMM GFLOPS (C=A^2)" if wl["square"] else "SpGEMM GFLOPS (C=A*B)", "value": gflops, "unit": "GFLOPS",
@@ -805,7 +810,8 @@ def main():
     ap.add_argument("--gather", default="fused", choices=["pipelined", "fused", "push"],
                     help="N > 1: how a rank's block of C reaches the peers (see nsparse_b200/multi_gpu.py)")
     ap.add_argument("--pieces", type=int, default=4)
-    ap.add_argument("--push-sms", type=int, default=0, help="N > 1: SMs of the pusher kernel (0: library default)")
+    ap.add_argument("--push-sms", type=int, default=0, help="N > 1, --gather-tma: SMs of the pusher kernel (0: library default)")
+    ap.add_argument("--gather-tma", action="store_true", help="N > 1: the TMA pusher kernel instead of the copy engines")
     ap.add_argument("--ip-partition", action="store_true", help="N > 1: keep the equal-intermediate-products row blocks")
     ap.add_argument("--nnz-weight", type=float, default=-1.0, help="N > 1: weight of nnz(C_i) in the row cost (default 0.25 (N-1))")
     ap.add_argument("--nccl-gather", action="store_true", help="N > 1: gather C with NCCL broadcasts instead of peer stores")

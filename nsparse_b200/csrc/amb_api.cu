@@ -7,9 +7,19 @@
 
 namespace {
 
-template <typename real>
-int free_arrays(nsp_amb *m)
+void forget_plan(nsp_context *ctx, const void *d_cs)
 {
+    auto it = ctx->amb_plans.find(d_cs);
+    if (it == ctx->amb_plans.end()) return;
+    cudaFree(it->second.d_mode);
+    cudaFree(it->second.d_zero_rows);
+    ctx->amb_plans.erase(it);
+}
+
+template <typename real>
+int free_arrays(nsp_context *ctx, nsp_amb *m)
+{
+    forget_plan(ctx, m->d_cs);
     cudaFree(m->d_cs);
     cudaFree(m->d_cl);
     cudaFree(m->d_sellcs_col);
@@ -92,7 +102,7 @@ int csr2amb(nsp_context *ctx, int M, int N, int nnz, const int *d_rpt, const int
             float ms = 0.f;
             long long tb = 256;
             const int rc = time_spmv<real>(ctx, &m, d_x, d_y, &ms, &tb);
-            free_arrays<real>(&m);
+            free_arrays<real>(ctx, &m);
             if (rc != 0) {
                 cudaFree(d_y);
                 return -1;
@@ -155,7 +165,7 @@ int nsp_amb_free(nsp_context *ctx, nsp_amb *mat)
     if (!ctx || !mat) return NSP_ERR_ARG;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    return free_arrays<float>(mat);
+    return free_arrays<float>(ctx, mat);
 }
 
 int nsp_spmv_amb_s(nsp_context *ctx, const nsp_amb *mat, const float *d_x, float *d_y)

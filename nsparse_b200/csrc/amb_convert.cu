@@ -28,6 +28,8 @@
 #include <vector>
 
 #include "../../include/nsparse_b200.h"
+#include <stdlib.h>
+
 #include "amb.h"
 #include "context.h"
 
@@ -428,6 +430,35 @@ int exclusive_sum(nsp_context *ctx, DevPool &pool, const T *in, T *out, long lon
     return 0;
 }
 
+// ---- write plan (nsp_amb_plan, context.h): how many virtual rows a row has, two mode bits per lane ----------
+__global__ void amb_row_vrows_kernel(const int *__restrict__ lane_cnt, const int *__restrict__ write_perm, long long lanes,
+                                     int M, int *__restrict__ row_nvr)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= lanes) return;
+    const int row = write_perm[i];
+    if (lane_cnt[i] > 0 && row < M) atomicAdd(row_nvr + row, 1);
+}
+
+__global__ void amb_mode_kernel(const int *__restrict__ lane_cnt, const int *__restrict__ write_perm, long long lanes, int M,
+                                const int *__restrict__ row_nvr, unsigned long long *__restrict__ mode)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // lanes is a multiple of 32
+    if (i >= lanes) return;
+    const int row = write_perm[i];
+    unsigned long long m = 0;
+    if (lane_cnt[i] > 0 && row < M) m = row_nvr[row] == 1 ? 2ull : 1ull;
+    m <<= 2 * (threadIdx.x & 31);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+    if ((threadIdx.x & 31) == 0) mode[i >> 5] = m;
+}
+
+struct AmbNotOne {
+    const int *nvr;
+    __device__ bool operator()(int i) const { return nvr[i] != 1; }
+};
+
 // Everything up to the lane table for one segment size.
 struct AmbLanes {
     const int *col = nullptr;      // CSR arrays the lanes index (original or key-sorted copy)
@@ -704,6 +735,39 @@ int amb_convert(nsp_context *ctx, int M, int N, int nnz, const int *rpt, const i
         NSP_CUDA_TRY(ctx, cudaMemcpyAsync(out->d_write_permutation, L.write_perm, sizeof(int) * lanes,
                                           cudaMemcpyDeviceToDevice, st));
         ctx->launches += 3;
+    }
+    // write plan of the SpMV (see nsp_amb_plan)
+    if (c_size > 0 && !getenv("NSPARSE_AMB_NO_PLAN")) {
+        nsp_amb_plan wp;
+        int *row_nvr = pool.take<int>((size_t)M + 1);
+        int *zr = pool.take<int>((size_t)M + 1);
+        int *d_nz = pool.take<int>(1);
+        if (!row_nvr || !zr || !d_nz) return -4;
+        NSP_CUDA_TRY(ctx, cudaMemsetAsync(row_nvr, 0, sizeof(int) * ((size_t)M + 1), st));
+        NSP_CUDA_TRY(ctx, cudaMalloc((void **)&wp.d_mode, sizeof(unsigned long long) * (size_t)c_size));
+        amb_row_vrows_kernel<<<blocks_for(lanes, 256), 256, 0, st>>>(L.lane_cnt, L.write_perm, lanes, M, row_nvr);
+        amb_mode_kernel<<<blocks_for(lanes, 256), 256, 0, st>>>(L.lane_cnt, L.write_perm, lanes, M, row_nvr, wp.d_mode);
+        ctx->launches += 2;
+        {
+            size_t bytes = 0;
+            thrust::counting_iterator<int> it(0);
+            AmbNotOne pred{row_nvr};
+            NSP_CUDA_TRY(ctx, cub::DeviceSelect::If(nullptr, bytes, it, zr, d_nz, M, pred, st));
+            void *tmp = pool.take<char>(bytes);
+            if (!tmp) return -4;
+            NSP_CUDA_TRY(ctx, cub::DeviceSelect::If(tmp, bytes, it, zr, d_nz, M, pred, st));
+        }
+        int nz = 0;
+        NSP_CUDA_TRY(ctx, cudaMemcpyAsync(&nz, d_nz, sizeof(int), cudaMemcpyDeviceToHost, st));
+        NSP_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        wp.n_zero_rows = nz;
+        if (nz > 0) {
+            NSP_CUDA_TRY(ctx, cudaMalloc((void **)&wp.d_zero_rows, sizeof(int) * (size_t)nz));
+            NSP_CUDA_TRY(ctx, cudaMemcpyAsync(wp.d_zero_rows, zr, sizeof(int) * (size_t)nz, cudaMemcpyDeviceToDevice, st));
+        }
+        wp.M = M;
+        wp.c_size = c_size;
+        ctx->amb_plans[out->d_cs] = wp;
     }
     NSP_CUDA_TRY(ctx, cudaGetLastError());
     NSP_CUDA_TRY(ctx, cudaStreamSynchronize(st));   // the pool's temporaries are freed on return

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256)
 amb_spmv_kernel(real *__restrict__ y, const real *__restrict__ value, const unsigned short *__restrict__ col,
                 const unsigned *__restrict__ cl, const int *__restrict__ cs, const real *__restrict__ x,
                 const unsigned short *__restrict__ perm, const unsigned short *__restrict__ perm_off, int lanes,
-                int seg_size, int M, int N)
+                int seg_size, int M, int N, const unsigned long long *__restrict__ mode)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= lanes) return;
@@ -68,12 +68,31 @@ amb_spmv_kernel(real *__restrict__ y, const real *__restrict__ value, const unsi
 #pragma unroll
         for (int b = 0; b < BS; ++b) acc += ld_stream(v + (h * BS + b) * 32) * ld_nc(x + min(cc + b, nmax));
     }
-    if (row < M) atomicAdd(y + row, acc);
+    if (mode) {
+        // write plan (nsp_amb_plan): 2 = this lane holds its whole row (plain store), 1 = the row has entries in
+        // several column segments (red into the zeroed entry), 0 = padding lane
+        const unsigned m = (unsigned)(ld_nc(reinterpret_cast<const long long *>(mode) + chunk) >> (2 * lane)) & 3u;
+        if (m == 2u)
+            y[row] = acc;
+        else if (m == 1u)
+            atomicAdd(y + row, acc);
+    } else if (row < M) {
+        atomicAdd(y + row, acc);
+    }
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256)
+amb_zero_rows_kernel(real *__restrict__ y, const int *__restrict__ rows, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[rows[i]] = real(0);
 }
 
 template <typename real, int BS>
 struct AmbLaunch {
-    static int run(nsp_context *ctx, const nsp_amb *mat, const real *x, real *y, int bs, int tb)
+    static int run(nsp_context *ctx, const nsp_amb *mat, const real *x, real *y, int bs, int tb,
+                   const unsigned long long *mode)
     {
         if (bs == BS) {
             const int lanes = mat->c_size * 32;
@@ -81,16 +100,16 @@ struct AmbLaunch {
             amb_spmv_kernel<real, BS><<<grid, tb, 0, ctx->stream>>>(
                 y, (const real *)mat->d_sellcs_val, mat->d_sellcs_col, mat->d_cl, mat->d_cs, x,
                 mat->d_s_write_permutation, mat->d_s_write_permutation_offset, lanes, (int)mat->seg_size, mat->M,
-                mat->N);
+                mat->N, mode);
             return 0;
         }
-        return AmbLaunch<real, BS + 1>::run(ctx, mat, x, y, bs, tb);
+        return AmbLaunch<real, BS + 1>::run(ctx, mat, x, y, bs, tb, mode);
     }
 };
 
 template <typename real>
 struct AmbLaunch<real, kAmbMaxBlock + 1> {
-    static int run(nsp_context *ctx, const nsp_amb *, const real *, real *, int bs, int)
+    static int run(nsp_context *ctx, const nsp_amb *, const real *, real *, int bs, int, const unsigned long long *)
     {
         return ctx->fail(-2, "nsp_spmv_amb: block_size " + std::to_string(bs) + " outside [1, 20]");
     }
@@ -101,11 +120,27 @@ int amb_spmv(nsp_context *ctx, const nsp_amb *mat, const real *x, real *y)
 {
     if (!mat || !y || (!x && mat->N > 0)) return ctx->fail(-2, "nsp_spmv_amb: bad argument");
     if (mat->M <= 0) return 0;
-    NSP_CUDA_TRY(ctx, cudaMemsetAsync(y, 0, sizeof(real) * (size_t)mat->M, ctx->stream));
+    // write plan: most rows live in ONE column segment and are written by a plain store; only the others need a
+    // zeroed y (the reference zeroes all of y in a kernel and adds every virtual row atomically,
+    // kernel_spmv_amb.cu:10-19, :70-76)
+    const unsigned long long *mode = nullptr;
+    auto it = ctx->amb_plans.find(mat->d_cs);
+    if (it != ctx->amb_plans.end() && mat->c_size > 0 && it->second.M == mat->M && it->second.c_size == mat->c_size) {
+        const nsp_amb_plan &wp = it->second;
+        mode = wp.d_mode;
+        if ((long long)wp.n_zero_rows * 3 > (long long)mat->M) {
+            NSP_CUDA_TRY(ctx, cudaMemsetAsync(y, 0, sizeof(real) * (size_t)mat->M, ctx->stream));
+        } else if (wp.n_zero_rows > 0) {
+            amb_zero_rows_kernel<real><<<(wp.n_zero_rows + 255) / 256, 256, 0, ctx->stream>>>(y, wp.d_zero_rows, wp.n_zero_rows);
+            ctx->launches += 1;
+        }
+    } else {
+        NSP_CUDA_TRY(ctx, cudaMemsetAsync(y, 0, sizeof(real) * (size_t)mat->M, ctx->stream));
+    }
     if (mat->c_size <= 0) return 0;
     int tb = (int)mat->thread_block;
     if (tb < 32 || tb > 256 || (tb & 31)) tb = 256;
-    if (AmbLaunch<real, 1>::run(ctx, mat, x, y, mat->block_size, tb) != 0) return -2;
+    if (AmbLaunch<real, 1>::run(ctx, mat, x, y, mat->block_size, tb, mode) != 0) return -2;
     ctx->launches += 1;
     NSP_CUDA_TRY(ctx, cudaGetLastError());
     return 0;

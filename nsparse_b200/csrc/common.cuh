@@ -25,34 +25,41 @@ constexpr int kEmptyKey = -1;              // columns are >= 0, so -1 marks a fr
 // the SpGEMM does not depend on the hash.
 constexpr unsigned kHashMul = 0x9E3779B1u;
 
-// Multi-GPU allgatherv of C, overlapped with the numeric phase (peer_push.cu).  Every GPU holds the FULL
-// C.col / C.val arrays; the bases of the other GPUs' copies are mapped into this process (CUDA IPC, or plain
-// peer access inside one process) and `off` is the element displacement of this rank's row block in them.
-// The block is cut into TILES of 2^kTileLog consecutive entries, aligned in the full arrays.  The numeric
-// kernels only COUNT: whoever has written entries [s, e) of the block adds the overlap to the counter of every
-// tile it touches (tiles_done below), and the thread that completes a tile appends it to a ready queue.  A
-// persistent pusher kernel on a few SMs of its own (push_tiles_kernel) takes the ready tiles in completion
-// order and moves them into every peer with the TMA alone (cp.async.bulk global -> shared -> peer global), so the NVLink
-// transfer runs next to the compute instead of inside the computing CTAs.  n == 0: single GPU.
+// Multi-GPU allgatherv of C, overlapped with the numeric phase.  Every GPU holds the FULL C.col / C.val arrays; the
+// bases of the other GPUs' copies are mapped into this process (CUDA IPC, or plain peer access inside one process)
+// and `off` is the element displacement of this rank's row block in them.  The block is cut into TILES of
+// 2^tile_log consecutive entries, aligned in the full arrays.  The numeric kernels only COUNT: whoever has written
+// entries [s, e) of the block adds the overlap to the counter of every tile it touches (tiles_done below); the
+// thread that completes a tile hands it on, and something that is NOT a computing SM moves it to the peers:
+//   * default (peer_dma.cu): tiles of 2^24 .. 2^26 entries, heavy rows processed tile by tile; the completing thread
+//     raises a flag in host-mapped memory, the host thread that issued the product polls the flags and gives every
+//     finished tile to the copy engines (cudaMemcpyAsync to each peer on its own stream);
+//   * option "gather_tma" (peer_push.cu): tiles of 4096 entries in a ready queue, a persistent pusher kernel on a few
+//     SMs of its own moves them with the TMA alone (cp.async.bulk global -> shared -> peer global).  Measured: one SM
+//     sustains only ~8-15 GB/s of remote stores, so saturating NVLink needs a third of the GPU
+//     (profiles/r2_bench_g2_pusher_*.json).
+// n == 0: single GPU.
 constexpr int kMaxPeerOut = 7;
-constexpr int kTileLog = 12;               // 4096 entries: 16 KiB of C.col + 16 / 32 KiB of C.val per tile
+constexpr int kTileLog = 12;               // pusher tiles: 4096 entries, 16 KiB of C.col + 16 / 32 KiB of C.val
 struct PeerOut {
     int n = 0;
     long long off = 0;
     int *col[kMaxPeerOut] = {};
     void *val[kMaxPeerOut] = {};
-    long long tile0 = 0;        // index of the first tile of the block (off >> kTileLog)
+    int tile_log = kTileLog;
+    long long tile0 = 0;        // index of the first tile of the block (off >> tile_log)
     int ntiles = 0;
     long long nnz = 0;          // entries of the block
     int *tile_cnt = nullptr;    // [ntiles] entries written so far
-    int *queue = nullptr;       // [ntiles] ready tiles (block relative), -1 = not yet published
-    int *q_ctl = nullptr;       // [0] tail (producers), [1] head (pusher tickets), [2] error flag
+    int *queue = nullptr;       // pusher: [ntiles] ready tiles (block relative), -1 = not yet published
+    int *q_ctl = nullptr;       // pusher: [0] tail (producers), [1] head (pusher tickets), [2] error flag
+    int *done = nullptr;        // copy engines: [ntiles] flags in host-mapped memory
 };
 
 // entries the block [off, off + nnz) has in its tile t (block relative)
 __host__ __device__ __forceinline__ int tile_len(const PeerOut &p, int t)
 {
-    const long long lo = (p.tile0 + t) << kTileLog, hi = lo + (1ll << kTileLog);
+    const long long lo = (p.tile0 + t) << p.tile_log, hi = lo + (1ll << p.tile_log);
     const long long a = lo > p.off ? lo : p.off, b = hi < p.off + p.nnz ? hi : p.off + p.nnz;
     return (int)(b - a);
 }
@@ -66,15 +73,20 @@ __device__ __forceinline__ void tiles_done(const PeerOut &p, long long first, lo
     if (count <= 0) return;
     __threadfence();
     const long long s = p.off + first, e = s + count;
-    for (long long t = s >> kTileLog; t <= (e - 1) >> kTileLog; ++t) {
-        const long long lo = t << kTileLog, hi = lo + (1ll << kTileLog);
+    for (long long t = s >> p.tile_log; t <= (e - 1) >> p.tile_log; ++t) {
+        const long long lo = t << p.tile_log, hi = lo + (1ll << p.tile_log);
         const int add = (int)((e < hi ? e : hi) - (s > lo ? s : lo));
         const int ti = (int)(t - p.tile0);
         const int old = atomicAdd(p.tile_cnt + ti, add);
         if (old + add == tile_len(p, ti)) {
-            __threadfence();                                  // the other writers' entries (seen through the counter)
-            const int slot = atomicAdd(p.q_ctl, 1);
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.queue + slot), "r"(ti) : "memory");
+            if (p.done) {
+                __threadfence_system();                       // every writer's entries, before the host sees the flag
+                *reinterpret_cast<volatile int *>(p.done + ti) = 1;
+            } else {
+                __threadfence();                              // the other writers' entries (seen through the counter)
+                const int slot = atomicAdd(p.q_ctl, 1);
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.queue + slot), "r"(ti) : "memory");
+            }
         }
     }
 }

@@ -165,13 +165,17 @@ void release_cpu_amb(sfAMB mat)
 
 void release_amb(sfAMB mat)
 {
-    cudaFree(mat.d_cs);
-    cudaFree(mat.d_cl);
-    cudaFree(mat.d_sellcs_val);
-    cudaFree(mat.d_sellcs_col);
-    cudaFree(mat.d_write_permutation);
-    cudaFree(mat.d_s_write_permutation);
-    cudaFree(mat.d_s_write_permutation_offset);
+    // the seven arrays (cudaFree, like nsparse.cu:226-235) and the SpMV write plan the library keeps for them
+    nsp_amb core;
+    memset(&core, 0, sizeof(core));
+    core.d_cs = mat.d_cs;
+    core.d_cl = mat.d_cl;
+    core.d_sellcs_col = mat.d_sellcs_col;
+    core.d_sellcs_val = mat.d_sellcs_val;
+    core.d_s_write_permutation = mat.d_s_write_permutation;
+    core.d_s_write_permutation_offset = mat.d_s_write_permutation_offset;
+    core.d_write_permutation = mat.d_write_permutation;
+    nsp_amb_free(the_context(), &core);
 }
 
 // ---- CPU SpMV and the two comparators (nsparse.cu:240-353) ----------------------------------------------

@@ -112,6 +112,7 @@ int context_destroy(nsp_context *ctx)
         cudaEventDestroy(ctx->ev_push_join);
     }
     cudaFree(ctx->d_push_ws);
+    nsp::peer_dma_destroy(ctx);
     cudaFree(ctx->d_seg);
     if (ctx->mem_pool) cudaMemPoolDestroy(ctx->mem_pool);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);

@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -45,6 +46,30 @@ struct nsp_host_result {
     int in_val_bytes = 0;
     int *d_cut_rows = nullptr;        // row cuts of nsp_spgemm_host_stream_* (65 entries each)
     long long *d_cut_offs = nullptr;
+};
+
+// How the lanes of an AMB matrix write y (amb_convert.cu builds it, amb_spmv.cu uses it; keyed by the matrix's d_cs
+// so that neither sfAMB nor nsp_amb -- fixed layouts -- has to carry it).  Per chunk two bits per lane: 0 = the lane
+// pads the chunk (nothing to write), 1 = its row has entries in several column segments (red.global into a zeroed
+// y), 2 = the lane holds the WHOLE row (plain store, no zeroing, no read-modify-write).  zero_rows: the rows that
+// are not written by a plain store (several virtual rows, or none at all).
+struct nsp_amb_plan {
+    unsigned long long *d_mode = nullptr;
+    int *d_zero_rows = nullptr;
+    int n_zero_rows = 0;
+    int M = 0, c_size = 0;        // of the matrix the plan was made for (checked before use)
+};
+
+// copy-engine gather of the multi-GPU SpGEMM (peer_dma.cu)
+struct nsp_dma_push {
+    int *d_tile_cnt = nullptr;
+    int *h_done = nullptr, *d_done = nullptr;     // tile flags: pinned host memory and its device alias
+    size_t cap = 0;
+    cudaStream_t copy_st[nsp::kMaxPeerOut] = {};
+    cudaEvent_t ev_copy[nsp::kMaxPeerOut] = {};
+    char *d_sort = nullptr;                       // keys / values / temporary storage of order_rows_by_tile
+    size_t sort_bytes = 0;
+    bool active = false;
 };
 
 struct nsp_prof_rec {
@@ -98,6 +123,9 @@ struct nsp_context {
 
     nsp_spgemm_state sp;
     nsp::PeerOut peer_out;   // nsp_spgemm_set_peers
+    nsp_dma_push dma;
+    long long opt_gather_tma = 0;        // 1: the TMA pusher kernel (peer_push.cu) instead of the copy engines
+    long long opt_dma_tile_log = 0;      // > 0: log2 of the copy-engine tile (tests)
     nsp::PeerOut last_push;  // the tile hand-off of the last product (diagnostics of nsp_spgemm_peers_status)
     // tile hand-off + pusher kernel of the multi-GPU allgatherv (peer_push.cu)
     cudaStream_t push_stream = nullptr;
@@ -109,6 +137,7 @@ struct nsp_context {
     bool peers_preloaded[2] = {false, false};   // numeric kernels loaded ahead of the pusher (fp32, fp64)
     long long opt_push_sms = 0;          // CTAs (= SMs) of the pusher kernel (0: default 16)
     nsp_host_result host;
+    std::unordered_map<const void *, nsp_amb_plan> amb_plans;
 
     long long launches = 0;
     std::string err;
@@ -178,10 +207,17 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
 // everything the numeric phase with peers would allocate or load lazily, done ahead (single-process multi-GPU:
 // see peer_push_reserve)
 template <typename real>
-int spgemm_numeric_reserve(nsp_context *ctx, int N, long long a_nnz, long long nnz_block);
+int spgemm_numeric_reserve(nsp_context *ctx, int N, long long a_nnz, long long nnz_block, int rows, int npeers);
 int rpt64_to_rpt32(nsp_context *ctx, int M, const long long *rpt64, long long nnz, int *rpt32);
 // peer_push.cu
 int peer_push_reserve(nsp_context *ctx, long long ntiles);
+// peer_dma.cu
+int dma_tile_log(long long nnz);
+int peer_dma_reserve(nsp_context *ctx, long long ntiles, int npeers, int max_rows);
+int peer_dma_begin(nsp_context *ctx, long long nnz_block);
+int peer_dma_drive(nsp_context *ctx, const int *c_col_full, const void *c_val_full, int val_bytes);
+int order_rows_by_tile(nsp_context *ctx, int *row_perm, int n, const long long *c_rpt, long long off, int tile_log);
+void peer_dma_destroy(nsp_context *ctx);
 int peer_push_begin(nsp_context *ctx, const int *c_col_full, const void *c_val_full, int val_bytes, long long nnz_block);
 int peer_push_end(nsp_context *ctx);
 

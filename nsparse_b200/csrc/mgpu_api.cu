@@ -199,7 +199,8 @@ int mgpu_numeric(nsp_mgpu *mg, long long *const *c_rpt64, int *const *c_col, rea
     // pusher kernel starts spinning anywhere -- cudaMalloc on one GPU of a process with peer access enabled
     // synchronises with its peers, i.e. it would wait for their pushers, which wait for kernels queued behind it.
     for_each_gpu(mg, [&](int g) -> int {
-        return nsp::spgemm_numeric_reserve<real>(mg->ctx[g], mg->N, mg->d[g].a_nnz, mg->d[g].nnz);
+        return nsp::spgemm_numeric_reserve<real>(mg->ctx[g], mg->N, mg->d[g].a_nnz, mg->d[g].nnz, mg->cuts[g + 1] - mg->cuts[g],
+                                                 mg->n - 1);
     });
     if (int rc = first_error(mg, "numeric phase (reserve)")) return rc;
     for_each_gpu(mg, [&](int g) -> int {

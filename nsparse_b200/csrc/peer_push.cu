@@ -224,6 +224,8 @@ int peer_push_begin(nsp_context *ctx, const int *c_col_full, const void *c_val_f
 {
     PeerOut &po = ctx->peer_out;
     po.nnz = nnz_block;
+    po.tile_log = kTileLog;
+    po.done = nullptr;
     po.tile0 = po.off >> kTileLog;
     po.ntiles = nnz_block > 0 ? (int)(((po.off + nnz_block - 1) >> kTileLog) - po.tile0 + 1) : 0;
     ctx->push_active = false;

@@ -615,7 +615,7 @@ static int preload_numeric_kernels(nsp_context *ctx)
 }
 
 template <typename real>
-int spgemm_numeric_reserve(nsp_context *ctx, int N, long long a_nnz, long long nnz_block)
+int spgemm_numeric_reserve(nsp_context *ctx, int N, long long a_nnz, long long nnz_block, int rows, int npeers)
 {
     if (preload_numeric_kernels<real>(ctx) != 0) return -1;
     int ws_max = ctx->opt_num_window_shift > 0 ? (int)ctx->opt_num_window_shift : 19;
@@ -624,7 +624,8 @@ int spgemm_numeric_reserve(nsp_context *ctx, int N, long long a_nnz, long long n
     while (wshift < ws_max && (1ll << wshift) < (long long)N) ++wshift;
     const long long nwin = ((long long)N + (1ll << wshift) - 1) >> wshift;
     if (nwin <= 4 && !ctx->opt_no_seg && reserve_entry_segments(ctx, a_nnz, (int)nwin) != 0) return -1;
-    return peer_push_reserve(ctx, (nnz_block >> kTileLog) + 2);
+    if (ctx->opt_gather_tma) return peer_push_reserve(ctx, (nnz_block >> kTileLog) + 2);
+    return peer_dma_reserve(ctx, (nnz_block >> dma_tile_log(nnz_block)) + 2, npeers, rows);
 }
 
 template <typename real>
@@ -708,9 +709,17 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
     long long nnz_block = 0;
     for (int b = 0; b < kNumBins; ++b) nnz_block += (long long)sp.h_binsum[kSumCnt + b];
     // multi-GPU: the pusher kernel takes its SMs first (peer_push.cu); the computing kernels only count tiles
-    if (peers && preload_numeric_kernels<real>(ctx) != 0) return -1;
-    if (peers && peer_push_begin(ctx, c_col - ctx->peer_out.off, c_val - ctx->peer_out.off, (int)sizeof(real), nnz_block) != 0)
-        return -1;
+    const bool tma = peers && ctx->opt_gather_tma;
+    if (tma) {
+        if (preload_numeric_kernels<real>(ctx) != 0) return -1;
+        if (peer_push_begin(ctx, c_col - ctx->peer_out.off, c_val - ctx->peer_out.off, (int)sizeof(real), nnz_block) != 0) return -1;
+    } else if (peers) {
+        // copy-engine gather: big tiles, and the heavy rows in tile order so that tiles finish one after another
+        if (peer_dma_begin(ctx, nnz_block) != 0) return -1;
+        if (order_rows_by_tile(ctx, sp.d_row_perm, num_imin(num_rows_in(sp, bm_bin, kNumBins - 1), 0x7fffffff), c_rpt64,
+                               ctx->peer_out.off, ctx->peer_out.tile_log) != 0)
+            return -1;
+    }
     const int push_sms = ctx->push_active ? ctx->push_ctas : 0;
 
     auto launch_bitmap = [&]() -> int {
@@ -812,7 +821,8 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
         NSP_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
         sp.join_pending = false;
     }
-    if (peers && peer_push_end(ctx) != 0) return -1;
+    if (tma && peer_push_end(ctx) != 0) return -1;
+    if (peers && !tma && peer_dma_drive(ctx, c_col - ctx->peer_out.off, c_val - ctx->peer_out.off, (int)sizeof(real)) != 0) return -1;
     return 0;
 }
 

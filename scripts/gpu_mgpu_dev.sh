@@ -18,5 +18,5 @@ PY
   tail -3 gpurun_out/r2_bench_g${N}_$tag.err | cut -c1-300
 }
 run_bench default --cpu-seconds 5 "$@"
-run_bench sms8 --no-cpu --no-check --push-sms 8 "$@"
-run_bench sms32 --no-cpu --no-check --push-sms 32 "$@"
+run_bench ip --no-cpu --no-check --ip-partition "$@"
+run_bench tma32 --no-cpu --no-check --gather-tma --push-sms 32 "$@"

@@ -384,16 +384,23 @@ def test_host_drain_fold(ns, ctx):
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("offset", [0, 12345])
-def test_tile_pusher_on_one_gpu(ns, ctx, dtype, offset):
-    """The multi-GPU allgatherv path (tile counters in every numeric kernel + the TMA pusher kernel, csrc/peer_push.cu)
-    with the 'peer' being a second buffer on the SAME GPU: after the product the peer copy must equal C entry for
-    entry at the block's displacement, and nothing outside the block may have been touched."""
+@pytest.mark.parametrize("mode", ["dma", "dma_small_tiles", "tma"])
+def test_tile_pusher_on_one_gpu(ns, dtype, offset, mode):
+    """The multi-GPU allgatherv path (tile counters in every numeric kernel, then either the copy engines driven by
+    the polling host thread, csrc/peer_dma.cu, or the TMA pusher kernel, csrc/peer_push.cu) with the 'peer' being a
+    second buffer on the SAME GPU: after the product the peer copy must equal C entry for entry at the block's
+    displacement, and nothing outside the block may have been touched."""
     import ctypes as C
 
     import torch
 
     from nsparse_b200 import gen
 
+    ctx = ns.Context(0)
+    if mode == "tma":
+        ctx.set_option("gather_tma", 1)
+    if mode == "dma_small_tiles":
+        ctx.set_option("dma_tile_log", 12)
     a = gen.rmat_csr(13, 16, seed=4, dtype=dtype, values="small_int")
     a.memcpy()
     d_rpt64, nnz, _ = ns.spgemm_symbolic(a, a, ctx)
@@ -416,3 +423,4 @@ def test_tile_pusher_on_one_gpu(ns, ctx, dtype, offset):
     assert np.array_equal(val[offset:offset + nnz].cpu().numpy(), want[2])
     assert torch.equal(pcol, col) and torch.equal(pval, val)
     assert int((pcol[:offset] != -7).sum()) == 0 and int((pcol[offset + nnz:] != -7).sum()) == 0
+    ctx.close()
