@@ -440,15 +440,16 @@ def run_ours(args):
 
     for w in range(args.warmup):
         c = step()
-        if w == 0 and world > 1 and not args.ip_partition and not wl["on_device"]:
-            # Re-cut the row blocks with the counts of the first product: a rank's time is its compute
-            # (~ intermediate products) plus what it sends (~ its entries of C times the peers), see
-            # partition_rows_by_cost.  Legitimate for repeated products on one pattern (the benchmark's case);
-            # a one-shot call only has the equal-products cut (--ip-partition).
-            c_rpt = c.d_rpt64.cpu().numpy()
+        if w < args.warmup - 1 and world > 1 and not args.ip_partition and not wl["on_device"] and peers is not None and peers.fused:
+            # Re-cut the row blocks from what the ranks needed for the product just made (partition_rows_by_measured):
+            # legitimate for repeated products on one pattern (the benchmark's case); a one-shot call only has the
+            # equal-products cut (--ip-partition).
             del c
-            weight = args.nnz_weight if args.nnz_weight >= 0 else 0.25 * (world - 1)
-            cuts, _ = ns.partition_rows_by_cost(a.rpt, a.col, b.rpt, c_rpt, world, weight)
+            mine = torch.tensor([peers.last_compute_s], dtype=torch.float64, device=dev)
+            allt = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+            dist.all_gather(allt, mine)
+            secs = [float(x.item()) for x in allt]
+            cuts, _ = ns.partition_rows_by_measured(a.rpt, a.col, b.rpt, cuts, secs, world)
             a_loc = ns.row_block(a, cuts[rank], cuts[rank + 1])
             a_loc.memcpy(local)
         c = None
@@ -651,8 +652,9 @@ def run_ours(args):
         if per_rank is not None:
             line["config"]["per_rank"] = per_rank
             line["config"]["partition"] = ("equal intermediate products" if (args.ip_partition or wl["on_device"]) else
-                                           "intermediate products + w * nnz(C_i), counts from the first warm-up product "
-                                           "(repeated products on one pattern; a one-shot call has the equal-products cut)")
+                                           "feedback: rows charged their intermediate products at the rate their block was "
+                                           "computed at in the previous warm-up product (partition_rows_by_measured; repeated "
+                                           "products on one pattern -- a one-shot call has the equal-products cut)")
         if gather is not None:
             line["gather"] = gather
         if ref_gpu is not None:

@@ -57,7 +57,14 @@ int context_create(nsp_context **out, int device)
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
     ctx->stream = nullptr;
-    if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // The side stream of the long rows gets the HIGHEST priority: its launch and the main launch of the heavy class
+    // become runnable at the same moment (both wait for the same predecessor), and which of the two the block
+    // scheduler served first used to depend on such things as an event record queued in between -- with the main
+    // launch first, the few long rows ran last and alone (measured: 80 ms instead of 25 ms for their launch, and no
+    // tile of C finished before the end, profiles/r2_trace_dma_order_priority.txt).
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;

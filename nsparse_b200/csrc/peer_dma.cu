@@ -14,6 +14,8 @@
 //       host-mapped memory; the host thread that called the numeric phase polls the flags while the kernels run
 //       and hands every finished tile to cudaMemcpyAsync, one stream per peer (peer_dma_drive).  The call returns
 //       when every tile has been issued; the context's stream then waits for the copy streams.
+#include <stdlib.h>
+
 #include <chrono>
 #include <thread>
 
@@ -156,6 +158,13 @@ int peer_dma_drive(nsp_context *ctx, const int *c_col_full, const void *c_val_fu
     std::vector<char> sent((size_t)nt, 0);
     int nsent = 0, first = 0;
     auto last = std::chrono::steady_clock::now();
+    // NSP_DMA_TRACE=1: when (ms after the start of the polling) the tiles were seen finished and when the kernels /
+    // the copies ended -- the timeline of the overlap without a profiler
+    const bool trace = getenv("NSP_DMA_TRACE") != nullptr;
+    const auto t_begin = last;
+    std::vector<float> seen_ms;
+    double kernels_done_ms = -1;
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(t - t_begin).count(); };
     volatile int *done = dp.h_done;
     const char *cv = static_cast<const char *>(c_val_full);
     while (nsent < nt) {
@@ -175,10 +184,13 @@ int peer_dma_drive(nsp_context *ctx, const int *c_col_full, const void *c_val_fu
             }
             for (int k = t; k <= t1; ++k) sent[k] = 1;
             nsent += t1 - t + 1;
+            if (trace)
+                for (int k = t; k <= t1; ++k) seen_ms.push_back((float)ms_since(std::chrono::steady_clock::now()));
             any = true;
             t = t1;
         }
         while (first < nt && sent[first]) ++first;
+        if (trace && kernels_done_ms < 0 && cudaStreamQuery(ctx->stream) == cudaSuccess) kernels_done_ms = ms_since(std::chrono::steady_clock::now());
         if (any) {
             last = std::chrono::steady_clock::now();
         } else {
@@ -197,6 +209,20 @@ int peer_dma_drive(nsp_context *ctx, const int *c_col_full, const void *c_val_fu
     for (int p = 0; p < po.n; ++p) {
         NSP_CUDA_TRY(ctx, cudaEventRecord(dp.ev_copy[p], dp.copy_st[p]));
         NSP_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, dp.ev_copy[p], 0));
+    }
+    if (trace && !seen_ms.empty()) {
+        const double issued_ms = ms_since(std::chrono::steady_clock::now());
+        if (kernels_done_ms < 0) {
+            // (the stream now also waits for the copies: time the kernels by the last flag instead)
+            kernels_done_ms = seen_ms.back();
+        }
+        for (int p = 0; p < po.n; ++p) cudaStreamSynchronize(dp.copy_st[p]);
+        const double copies_ms = ms_since(std::chrono::steady_clock::now());
+        const size_t n = seen_ms.size();
+        fprintf(stderr, "[nsp dma] dev %d: %d tiles of 2^%d entries; flags seen at %.1f / %.1f / %.1f / %.1f / %.1f ms (first, 25%%, 50%%, 75%%, "
+                        "last); kernels done %.1f ms; all copies issued %.1f ms, landed %.1f ms\n",
+                ctx->device, nt, po.tile_log, seen_ms[0], seen_ms[n / 4], seen_ms[n / 2], seen_ms[3 * n / 4], seen_ms[n - 1], kernels_done_ms,
+                issued_ms, copies_ms);
     }
     return 0;
 }

@@ -722,8 +722,9 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
     }
     const int push_sms = ctx->push_active ? ctx->push_ctas : 0;
 
-    auto launch_bitmap = [&]() -> int {
+    auto launch_bitmap = [&](int multi) -> int {
         if (num_rows_in(sp, bm_bin, kNumBins - 1) == 0) return 0;
+        if (multi && !sp.has_multi_slab) return 0;
         if (cap < 128 || ((1ll << wshift) + cap - 1) / cap > kMaxChunks)
             return ctx->fail(-4, "nsp_spgemm_numeric: shared memory too small for the bitmap kernel");
         const size_t smem = fixed + (size_t)cap * (sizeof(real) + sizeof(int));
@@ -745,31 +746,28 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
         // The long rows (few, each with millions of products: a tail of a handful of CTAs) go to a side stream
         // and start first; as their CTAs retire, the SMs pick up the CTAs of the main launch, whose dynamic row
         // queue balances whatever number of them is running.  Joined at the end of the phase.
-        bool forked = false;
-        for (int multi = 1; multi >= 0; --multi) {
-            if (multi && !sp.has_multi_slab) continue;
-            auto kern = kerns[multi][peers ? 1 : 0][mode];
-            NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            cudaStream_t st = ctx->stream;
-            if (multi && !ctx->opt_no_fork) {
-                NSP_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-                NSP_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
-                st = ctx->aux_stream;
-                forked = true;
-            }
-            ctx->prof_on_aux = st != ctx->stream;
-            num_prof_class(ctx, multi ? "num_bitmap_long" : "num_bitmap", bm_bin, kNumBins - 1);
-            kern<<<grid, 1024, smem, st>>>(NSP_NUM_ARGS, bm_bin, kNumBins - 1, multi ? 5 : 4, N, wshift, cap,
-                                           b_vec_end_of(ctx, b_col), (int)ctx->opt_debug,
-                                           ctx->opt_phase_timing ? ctx->phase_cycles() : nullptr, use_seg ? ctx->d_seg : nullptr,
-                                           a_entries, ctx->peer_out);
-            ctx->prof_end();
-            ctx->prof_on_aux = false;
-            ctx->launches += 1;
-            NSP_CUDA_TRY(ctx, cudaGetLastError());
+        auto kern = kerns[multi][peers ? 1 : 0][mode];
+        NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaStream_t st = ctx->stream;
+        if (multi && !ctx->opt_no_fork) {
+            NSP_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+            NSP_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+            st = ctx->aux_stream;
         }
-        if (forked) NSP_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
-        sp.join_pending = forked;
+        ctx->prof_on_aux = st != ctx->stream;
+        num_prof_class(ctx, multi ? "num_bitmap_long" : "num_bitmap", bm_bin, kNumBins - 1);
+        kern<<<grid, 1024, smem, st>>>(NSP_NUM_ARGS, bm_bin, kNumBins - 1, multi ? 5 : 4, N, wshift, cap,
+                                       b_vec_end_of(ctx, b_col), (int)ctx->opt_debug,
+                                       ctx->opt_phase_timing ? ctx->phase_cycles() : nullptr, use_seg ? ctx->d_seg : nullptr,
+                                       a_entries, ctx->peer_out);
+        ctx->prof_end();
+        ctx->prof_on_aux = false;
+        ctx->launches += 1;
+        NSP_CUDA_TRY(ctx, cudaGetLastError());
+        if (st != ctx->stream) {
+            NSP_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+            sp.join_pending = true;
+        }
         return 0;
     };
     auto launch_light = [&]() -> int {
@@ -809,13 +807,16 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
         }
         return 0;
     };
-    // One GPU: heaviest class first, the light classes fill the tail of the heavy launch.  Multi-GPU: a tile of C
-    // can leave for the peers once ALL rows that overlap it are done, so the (short) light classes go first and
-    // the heavy launch then completes tiles steadily while it runs.
+    // One GPU: heaviest class first (the long rows on their side stream, then the main launch), the light classes fill
+    // the tail.  Multi-GPU: a tile of C can leave for the peers once ALL rows that overlap it are done, so the long
+    // rows start at once (nothing is queued ahead of them: if they had to wait for the light classes next to the main
+    // launch, whichever of the two the hardware released first took every SM -- measured: the long rows then ran last
+    // and no tile finished before the end), the (short) light classes follow and the main launch, which completes
+    // tiles steadily, comes last.
     if (peers) {
-        if (launch_light() != 0 || launch_bitmap() != 0) return -1;
+        if (launch_bitmap(1) != 0 || launch_light() != 0 || launch_bitmap(0) != 0) return -1;
     } else {
-        if (launch_bitmap() != 0 || launch_light() != 0) return -1;
+        if (launch_bitmap(1) != 0 || launch_bitmap(0) != 0 || launch_light() != 0) return -1;
     }
     if (sp.join_pending) {
         NSP_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));

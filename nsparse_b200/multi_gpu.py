@@ -58,6 +58,32 @@ def partition_rows_by_cost(a_rpt, a_col, b_rpt, c_rpt, nparts: int, nnz_weight: 
     return cuts, int(ip_prefix[-1])
 
 
+def partition_rows_by_measured(a_rpt, a_col, b_rpt, old_cuts, seconds, nparts: int):
+    """Feedback cut for REPEATED products on one pattern: `seconds[r]` is what rank r needed for its block
+    [old_cuts[r], old_cuts[r+1]) of the previous product.  Every row is charged its intermediate products divided by
+    the speed (products per second) its old block was computed at, and the new cuts split that cost evenly.
+    Power-law inputs need it: the hub rows at the top are computed at a different rate per product than the tail
+    (more windows and chunks per row, the rows with more than 1024 entries of A take the red.global path)."""
+    a_rpt = np.asarray(a_rpt, dtype=np.int64)
+    blen = np.diff(np.asarray(b_rpt, dtype=np.int64))
+    cs = np.concatenate([[0], np.cumsum(blen[np.asarray(a_col)])])
+    ip_prefix = cs[a_rpt].astype(np.float64)                  # products before each row
+    M = len(a_rpt) - 1
+    cost = np.zeros(M + 1, dtype=np.float64)
+    for r in range(len(old_cuts) - 1):
+        lo, hi = old_cuts[r], old_cuts[r + 1]
+        ip_r = ip_prefix[hi] - ip_prefix[lo]
+        per_product = (seconds[r] / ip_r) if ip_r > 0 else 0.0
+        cost[lo + 1:hi + 1] = cost[lo] + (ip_prefix[lo + 1:hi + 1] - ip_prefix[lo]) * per_product
+    cuts = [0]
+    for p in range(1, nparts):
+        cuts.append(int(np.searchsorted(cost, cost[-1] * p / nparts, side="left")))
+    cuts.append(M)
+    for i in range(1, len(cuts)):
+        cuts[i] = min(max(cuts[i], cuts[i - 1]), M)
+    return cuts, int(ip_prefix[-1])
+
+
 def partition_rows_by_ip_device(a, b, nparts: int):
     """partition_rows_by_ip for matrices that live on the GPU (nsparse_b200.gen.DeviceCSR): the same cuts, computed
     with torch on the device.  Returns (cuts, total_ip)."""
@@ -174,6 +200,7 @@ class PeerBuffers:
         self.cap_nnz, self.n_rows, self.dtype = -1, -1, None
         self.col = self.val = self.rpt = None
         self._own, self._opened = {}, []
+        self.last_compute_s = 0.0
 
     def _others(self, key):
         import torch.distributed as dist
@@ -307,8 +334,12 @@ def spgemm_kernel_hash_mgpu(a_local: CSR, b: CSR, cuts, n_rows: int, total_ip: i
 
     from .spgemm import spgemm_numeric, spgemm_symbolic
 
+    import time
+
     rank = dist.get_rank(group)
-    d_rpt64, nnz, _ = spgemm_symbolic(a_local, b, ctx)
+    t_start = time.perf_counter()
+    d_rpt64, nnz, _ = spgemm_symbolic(a_local, b, ctx)       # (synchronises: nnz comes back to the host)
+    t_own = time.perf_counter() - t_start
     dev = d_rpt64.device
     disp = _gather_sizes(nnz, dev, group)
     tot = int(disp[-1])
@@ -324,11 +355,15 @@ def spgemm_kernel_hash_mgpu(a_local: CSR, b: CSR, cuts, n_rows: int, total_ip: i
         if peers.fused:
             # the numeric kernels count finished tiles of C, the pusher kernel sends them to all peers meanwhile
             peers.set_fused_targets(lo)
+            t_num = time.perf_counter()
             try:
                 spgemm_numeric(a_local, b, d_rpt64, nnz, ctx, out=out)
             finally:
                 peers.clear_fused_targets()
             peers.check_status()
+            # copy-engine gather: the call returns when the last tile was handed over, i.e. when this rank's kernels
+            # are done -- the rank's own compute time, for partition_rows_by_measured
+            peers.last_compute_s = t_own + (time.perf_counter() - t_num)
         elif peers.pieces >= 1 and a_local.M > 0:
             # pipeline: piece k+1 is computed while the copy engines carry piece k to the peers
             main = torch.cuda.current_stream(dev)
