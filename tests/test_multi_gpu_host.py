@@ -116,3 +116,51 @@ def test_partition_rows_by_cost_balances_products_plus_output():
     cost = ip_row + w * np.diff(c_rpt)
     per = [cost[cuts[i]:cuts[i + 1]].sum() for i in range(4)]
     assert max(per) - min(per) <= 2 * cost.max() + 1e-9     # within one (heaviest) row of each other
+
+
+def test_partition_by_measured_times():
+    """Feedback cut: equal times keep the equal-products cut; a rank that was twice as slow gets about half the
+    products; cuts stay monotone and cover all rows."""
+    import numpy as np
+
+    import nsparse_b200 as ns
+    from nsparse_b200 import gen
+
+    a = gen.rmat_csr(12, 16, seed=3, dtype=np.float32)
+    cuts, ip = ns.partition_rows_by_ip(a.rpt, a.col, a.rpt, 4)
+    same, ip2 = ns.partition_rows_by_measured(a.rpt, a.col, a.rpt, cuts, [1.0] * 4, 4)
+    assert ip2 == ip and all(abs(x - y) <= 1 for x, y in zip(same, cuts))      # (float targets: a row either way)
+    new, _ = ns.partition_rows_by_measured(a.rpt, a.col, a.rpt, cuts, [2.0, 1.0, 1.0, 1.0], 4)
+    assert new[0] == 0 and new[-1] == a.M and all(x <= y for x, y in zip(new, new[1:]))
+    blen = np.diff(a.rpt).astype(np.int64)
+    row_ip = np.add.reduceat(np.r_[blen[a.col], 0], np.minimum(a.rpt[:-1], a.nnz))
+    row_ip[np.diff(a.rpt) == 0] = 0
+    share0_old = row_ip[:cuts[1]].sum() / ip
+    share0_new = row_ip[:new[1]].sum() / ip
+    assert 0.2 < share0_old < 0.3 and share0_new < 0.75 * share0_old
+
+
+def test_device_partition_and_generators_on_cpu_tensors():
+    """The torch versions used for the full-size C4 / C5 inputs (nsparse_b200.gen.*_device, partition_rows_by_ip_device)
+    are plain torch: on CPU tensors they must reproduce the numpy / native results bit for bit."""
+    import numpy as np
+    import torch
+
+    import nsparse_b200 as ns
+    from nsparse_b200 import gen
+
+    dev = torch.device("cpu")
+    d = gen.rmat_csr_device(11, 16, 12345, np.float64, dev)
+    h = gen.rmat_csr(11, 16, 12345, np.float64)
+    assert np.array_equal(d.d_rpt.numpy(), h.rpt) and np.array_equal(d.d_col.numpy(), h.col) and np.array_equal(d.d_val.numpy(), h.val)
+    assert ns.partition_rows_by_ip_device(d, d, 3) == ns.partition_rows_by_ip(h.rpt, h.col, h.rpt, 3)
+    blk, hb = ns.row_block(d, 100, 700), ns.row_block(h, 100, 700)
+    assert np.array_equal(blk.d_rpt.numpy(), hb.rpt) and np.array_equal(blk.d_col.numpy(), hb.col)
+    e = gen.er_csr_device(3000, 500, 4, device=dev)
+    c = e.d_col.numpy().reshape(3000, 4)
+    assert (np.diff(c, axis=1) > 0).all() and c.min() >= 0 and c.max() < 500
+    p = gen.powerlaw_csr_device(1 << 13, 64, 2048, device=dev)
+    lens = np.diff(p.d_rpt.numpy())
+    assert lens.max() == 2048 and lens.min() >= 1
+    sub = p.rows_to_host([0, 5, 77])
+    assert sub.M == 3 and sub.nnz == int(lens[[0, 5, 77]].sum())
