@@ -441,15 +441,17 @@ def run_ours(args):
     for w in range(args.warmup):
         c = step()
         if w < args.warmup - 1 and world > 1 and not args.ip_partition and not wl["on_device"] and peers is not None and peers.fused:
-            # Re-cut the row blocks from what the ranks needed for the product just made (partition_rows_by_measured):
+            # Re-cut the row blocks from what the ranks needed for the product just made and from what they have to send
+            # (partition_rows_minmax: a block costs max(compute, outbound transfer)):
             # legitimate for repeated products on one pattern (the benchmark's case); a one-shot call only has the
             # equal-products cut (--ip-partition).
+            c_rpt = c.d_rpt64.cpu().numpy()
             del c
             mine = torch.tensor([peers.last_compute_s], dtype=torch.float64, device=dev)
             allt = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
             dist.all_gather(allt, mine)
             secs = [float(x.item()) for x in allt]
-            cuts, _ = ns.partition_rows_by_measured(a.rpt, a.col, b.rpt, cuts, secs, world)
+            cuts, _ = ns.partition_rows_minmax(a.rpt, a.col, b.rpt, c_rpt, cuts, secs, world, 4 + V, args.out_gbs)
             a_loc = ns.row_block(a, cuts[rank], cuts[rank + 1])
             a_loc.memcpy(local)
         c = None
@@ -495,6 +497,10 @@ def run_ours(args):
     # -------- parity of a row sample against the CPU oracle + CPU baseline (rank 0) ----------------------------
     cpu, parity = None, None
     if rank == 0 and not args.no_cpu:
+        if world > 1:
+            from oracle import oracle as _orc
+
+            _orc.set_threads(max(1, (os.cpu_count() or 1) // 2))      # torchrun pins OMP_NUM_THREADS=1 for its workers
         if wl["on_device"]:
             # C4 / C5: a few hundred rows spread over the matrix (the full inputs never leave the GPU)
             src = a_loc if world > 1 else a
@@ -652,9 +658,10 @@ def run_ours(args):
         if per_rank is not None:
             line["config"]["per_rank"] = per_rank
             line["config"]["partition"] = ("equal intermediate products" if (args.ip_partition or wl["on_device"]) else
-                                           "feedback: rows charged their intermediate products at the rate their block was "
-                                           "computed at in the previous warm-up product (partition_rows_by_measured; repeated "
-                                           "products on one pattern -- a one-shot call has the equal-products cut)")
+                                           "feedback: a block costs max(compute, outbound transfer) -- rows charged their "
+                                           "intermediate products at the rate their block was computed at in the previous warm-up "
+                                           f"product, entries of C at {args.out_gbs:.0f} GB/s to the N-1 peers (partition_rows_minmax; "
+                                           "repeated products on one pattern -- a one-shot call has the equal-products cut)")
         if gather is not None:
             line["gather"] = gather
         if ref_gpu is not None:
@@ -815,7 +822,7 @@ def main():
     ap.add_argument("--push-sms", type=int, default=0, help="N > 1, --gather-tma: SMs of the pusher kernel (0: library default)")
     ap.add_argument("--gather-tma", action="store_true", help="N > 1: the TMA pusher kernel instead of the copy engines")
     ap.add_argument("--ip-partition", action="store_true", help="N > 1: keep the equal-intermediate-products row blocks")
-    ap.add_argument("--nnz-weight", type=float, default=-1.0, help="N > 1: weight of nnz(C_i) in the row cost (default 0.25 (N-1))")
+    ap.add_argument("--out-gbs", type=float, default=450.0, help="N > 1: outbound GB/s per GPU assumed by the row partition")
     ap.add_argument("--nccl-gather", action="store_true", help="N > 1: gather C with NCCL broadcasts instead of peer stores")
     ap.add_argument("--no-check", action="store_true", help="N > 1: skip the gather_ok check")
     ap.add_argument("--no-e2e", action="store_true")

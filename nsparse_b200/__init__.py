@@ -11,6 +11,6 @@ from .spgemm import (get_spgemm_flop, spgemm_kernel_hash, spgemm_numeric,   # no
                      spgemm_symbolic)
 from .amb import AMB, Plan, csr2amb, spmv_amb             # noqa: F401
 from .multi_gpu import (PeerBuffers, allgatherv_csr, partition_rows_by_cost, partition_rows_by_ip,   # noqa: F401
-                        partition_rows_by_ip_device, partition_rows_by_measured, row_block,
+                        partition_rows_by_ip_device, partition_rows_by_measured, partition_rows_minmax, row_block,
                         spgemm_kernel_hash_mgpu)
 from ._lib import NsparseError, load as load_library     # noqa: F401

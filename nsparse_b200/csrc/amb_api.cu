@@ -129,17 +129,24 @@ int spmv_host(nsp_context *ctx, const nsp_amb *mat, const real *h_x, real *h_y)
 {
     if (!ctx || !mat) return NSP_ERR_ARG;
     cudaSetDevice(ctx->device);
-    real *d_x = nullptr, *d_y = nullptr;
-    NSP_CUDA_TRY(ctx, cudaMalloc((void **)&d_x, sizeof(real) * (size_t)(mat->N > 0 ? mat->N : 1)));
-    NSP_CUDA_TRY(ctx, cudaMalloc((void **)&d_y, sizeof(real) * (size_t)(mat->M > 0 ? mat->M : 1)));
+    // x / y staging on the device: grow-only buffers of the context (an iterative solver calls this in a loop)
+    const size_t need = sizeof(real) * ((size_t)(mat->N > 0 ? mat->N : 1) + (size_t)(mat->M > 0 ? mat->M : 1)) + 256;
+    if (need > ctx->spmv_stage_bytes) {
+        NSP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_spmv_stage);
+        ctx->d_spmv_stage = nullptr;
+        ctx->spmv_stage_bytes = 0;
+        NSP_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_spmv_stage, need));
+        ctx->spmv_stage_bytes = need;
+    }
+    real *d_x = reinterpret_cast<real *>(ctx->d_spmv_stage);
+    real *d_y = reinterpret_cast<real *>(ctx->d_spmv_stage + ((sizeof(real) * (size_t)(mat->N > 0 ? mat->N : 1) + 255) & ~size_t(255)));
     cudaStream_t st = ctx->stream;
     int rc = 0;
     if (cudaMemcpyAsync(d_x, h_x, sizeof(real) * (size_t)mat->N, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = -1;
     if (rc == 0) rc = nsp::amb_spmv<real>(ctx, mat, d_x, d_y);
     if (rc == 0 && cudaMemcpyAsync(h_y, d_y, sizeof(real) * (size_t)mat->M, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
     if (cudaStreamSynchronize(st) != cudaSuccess) rc = -1;
-    cudaFree(d_x);
-    cudaFree(d_y);
     if (rc == -1 && ctx->err.empty()) ctx->fail(-1, "nsp_spmv_amb_host: CUDA copy failed");
     return rc;
 }

@@ -112,6 +112,7 @@ int nsp_set_option(nsp_context *ctx, const char *name, long long value)
     else if (!strcmp(name, "num_cap")) ctx->opt_num_cap = value;
     else if (!strcmp(name, "push_sms")) ctx->opt_push_sms = value;
     else if (!strcmp(name, "no_seg")) ctx->opt_no_seg = value;
+    else if (!strcmp(name, "no_flat")) ctx->opt_no_flat = value;
     else if (!strcmp(name, "gather_tma")) ctx->opt_gather_tma = value;
     else if (!strcmp(name, "dma_tile_log")) ctx->opt_dma_tile_log = value;
     else if (!strcmp(name, "sort")) ctx->opt_unsorted = value == 0;

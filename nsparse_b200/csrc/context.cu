@@ -121,6 +121,12 @@ int context_destroy(nsp_context *ctx)
     cudaFree(ctx->d_push_ws);
     nsp::peer_dma_destroy(ctx);
     cudaFree(ctx->d_seg);
+    cudaFree(ctx->d_spmv_stage);
+    for (auto &kv : ctx->amb_plans) {
+        cudaFree(kv.second.d_mode);
+        cudaFree(kv.second.d_zero_rows);
+    }
+    ctx->amb_plans.clear();
     if (ctx->mem_pool) cudaMemPoolDestroy(ctx->mem_pool);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);

@@ -99,6 +99,7 @@ struct nsp_context {
     int *d_seg = nullptr;
     size_t seg_cap = 0;
     long long opt_unsorted = 0;          // 1: sort = false numeric mode, the hash classes skip the per-row column sort
+    long long opt_no_flat = 0;           // 1: never the flat traversal of the heavy kernels; -1: always (tests)
     long long opt_no_seg = 0;            // 1: never use the segment mode (tests, A/B measurements)
 
     // options (nsp_set_option)
@@ -138,6 +139,8 @@ struct nsp_context {
     long long opt_push_sms = 0;          // CTAs (= SMs) of the pusher kernel (0: default 16)
     nsp_host_result host;
     std::unordered_map<const void *, nsp_amb_plan> amb_plans;
+    char *d_spmv_stage = nullptr;        // x / y of nsp_spmv_amb_host_* (grow-only)
+    size_t spmv_stage_bytes = 0;
 
     long long launches = 0;
     std::string err;

@@ -181,11 +181,12 @@ __device__ __forceinline__ int parts_of(int kb, int len)
     return len > 0 ? ((kb & 3) + len + kPartLen - 1) / kPartLen : 0;
 }
 
-// parts prefix of the staged segments; two barriers; returns the number of parts
-template <int BS, typename real>
+// parts prefix of the staged segments; two barriers; returns the number of parts.  kFlat (classes whose B rows are
+// short, see run_flat): the prefix counts PRODUCTS instead of parts.
+template <int BS, typename real, bool kFlat = false>
 __device__ __forceinline__ int scan_parts(int t, int kb, int len, PartScratch<BS, real> &s)
 {
-    const int np = parts_of(kb, len);
+    const int np = kFlat ? len : parts_of(kb, len);
     const int inc = group_inclusive_scan<BS>(np, t, s.wtot);
     s.pre[t + 1] = inc;
     if ((t & 31) == 0) s.pre1[t >> 5] = inc - np;
@@ -199,7 +200,7 @@ __device__ __forceinline__ int scan_parts(int t, int kb, int len, PartScratch<BS
 // is visited once per pass because the sub-range of each B row is found by binary search instead of
 // filtering.  use_lo / use_hi say which bounds actually cut (both false: the whole B row).
 // One thread per entry, both bounds from scratch: the path of rows with more than BS entries.
-template <int BS, bool kLoadVal, typename real>
+template <int BS, bool kLoadVal, typename real, bool kFlat = false>
 __device__ __forceinline__ int stage_parts_range(int t, int base, int a_end, const int *__restrict__ a_col,
                                                  const real *__restrict__ a_val, const int *__restrict__ b_rpt,
                                                  const int *__restrict__ b_col, int col_lo, int col_hi,
@@ -234,7 +235,7 @@ __device__ __forceinline__ int stage_parts_range(int t, int base, int a_end, con
     }
     s.kb[t] = kb;
     s.len[t] = len;
-    return scan_parts<BS, real>(t, kb, len, s);
+    return scan_parts<BS, real, kFlat>(t, kb, len, s);
 }
 
 // Lower bound by a GROUP of g = 2^glog lanes (g-ary search: ceil(log_{g+1} n) dependent loads instead
@@ -277,7 +278,7 @@ __device__ __forceinline__ int entry_group_log(int E, int BS)
 // the row (segments start at the B row's start), otherwise they start where the previous window ended
 // (s.end).  cut_hi: the window does not reach N, so the end is searched.  Leaves kb/len = the window
 // segment, cur = its start, end = its end, and the part prefix.
-template <int BS, bool kLoadVal, typename real>
+template <int BS, bool kLoadVal, typename real, bool kFlat = false>
 __device__ __forceinline__ int stage_window(int t, int a_beg, int E, int glog, const int *__restrict__ a_col,
                                             const real *__restrict__ a_val, const int *__restrict__ b_rpt,
                                             const int *__restrict__ b_col, int c1, bool first, bool cut_hi,
@@ -302,12 +303,12 @@ __device__ __forceinline__ int stage_window(int t, int a_beg, int E, int glog, c
         }
     }
     __syncthreads();
-    return scan_parts<BS, real>(t, t < E ? s.kb[t] : 0, t < E ? s.len[t] : 0, s);
+    return scan_parts<BS, real, kFlat>(t, t < E ? s.kb[t] : 0, t < E ? s.len[t] : 0, s);
 }
 
 // Chunk stage: segment [cur, first column >= col_hi) of every entry (last: up to the window end), and
 // the cursor moves on.
-template <int BS, typename real>
+template <int BS, typename real, bool kFlat = false>
 __device__ __forceinline__ int stage_chunk(int t, int E, int glog, const int *__restrict__ b_col, int col_hi,
                                            bool last, PartScratch<BS, real> &s)
 {
@@ -327,7 +328,7 @@ __device__ __forceinline__ int stage_chunk(int t, int E, int glog, const int *__
         }
     }
     __syncthreads();
-    return scan_parts<BS, real>(t, t < E ? s.kb[t] : 0, t < E ? s.len[t] : 0, s);
+    return scan_parts<BS, real, kFlat>(t, t < E ? s.kb[t] : 0, t < E ? s.len[t] : 0, s);
 }
 
 // ---- segment mode (B column-sorted, at most 4 windows): the window cuts of every B row are PRECOMPUTED per
@@ -336,7 +337,7 @@ __device__ __forceinline__ int stage_chunk(int t, int E, int glog, const int *__
 // loads per entry instead of the dependent chain a_col -> B.rpt -> search probes of stage_window, which was pure
 // exposed latency at the start of every window (profiles/r2_phase_cycles_num_bitmap_s20_baseline.txt: "mark
 // stage" 7 % of the kernel).
-template <int BS, bool kLoadVal, typename real>
+template <int BS, bool kLoadVal, typename real, bool kFlat = false>
 __device__ __forceinline__ int stage_window_seg(int t, int a_beg, int E, const real *__restrict__ a_val,
                                                 const int *__restrict__ seg, long long stride, int win, bool first,
                                                 PartScratch<BS, real> &s)
@@ -349,11 +350,11 @@ __device__ __forceinline__ int stage_window_seg(int t, int a_beg, int E, const r
         s.len[t] = hi - lo;
         if (kLoadVal && first) s.av[t] = ld_stream(a_val + a_beg + t);
     }
-    return scan_parts<BS, real>(t, lo, hi - lo, s);
+    return scan_parts<BS, real, kFlat>(t, lo, hi - lo, s);
 }
 
 // the same for one slab of a row with more than BS entries
-template <int BS, bool kLoadVal, typename real>
+template <int BS, bool kLoadVal, typename real, bool kFlat = false>
 __device__ __forceinline__ int stage_slab_seg(int t, int base, int a_end, const real *__restrict__ a_val,
                                               const int *__restrict__ seg, long long stride, int win,
                                               PartScratch<BS, real> &s)
@@ -366,7 +367,7 @@ __device__ __forceinline__ int stage_slab_seg(int t, int base, int a_end, const 
     }
     s.kb[t] = lo;
     s.len[t] = hi - lo;
-    return scan_parts<BS, real>(t, lo, hi - lo, s);
+    return scan_parts<BS, real, kFlat>(t, lo, hi - lo, s);
 }
 
 // All chunk boundaries of a window at once: tab[k * E + e], k = 0 .. nch, from the staged window segments
@@ -402,7 +403,7 @@ __device__ __forceinline__ void build_chunk_table(int t, int E, int nch, const i
 }
 
 // chunk k of the window from the table
-template <int BS, typename real>
+template <int BS, typename real, bool kFlat = false>
 __device__ __forceinline__ int stage_chunk_tab(int t, int E, int k, PartScratch<BS, real> &s)
 {
     int lo = 0, hi = 0;
@@ -412,12 +413,12 @@ __device__ __forceinline__ int stage_chunk_tab(int t, int E, int k, PartScratch<
         s.kb[t] = lo;
         s.len[t] = hi - lo;
     }
-    return scan_parts<BS, real>(t, lo, hi - lo, s);
+    return scan_parts<BS, real, kFlat>(t, lo, hi - lo, s);
 }
 
 // chunk [col_lo, col_hi) of the window when the table does not fit: both ends searched in the window segment,
 // which is re-read from the precomputed cuts (first / last: that end is the window's)
-template <int BS, typename real>
+template <int BS, typename real, bool kFlat = false>
 __device__ __forceinline__ int stage_chunk_seg(int t, int a_beg, int E, int glog, const int *__restrict__ b_col,
                                                const int *__restrict__ seg, long long stride, int win, int col_lo,
                                                int col_hi, bool first, bool last, PartScratch<BS, real> &s)
@@ -438,7 +439,7 @@ __device__ __forceinline__ int stage_chunk_seg(int t, int a_beg, int E, int glog
         }
     }
     __syncthreads();
-    return scan_parts<BS, real>(t, t < E ? s.kb[t] : 0, t < E ? s.len[t] : 0, s);
+    return scan_parts<BS, real, kFlat>(t, t < E ? s.kb[t] : 0, t < E ? s.len[t] : 0, s);
 }
 
 // entry of part q = largest e with pre[e] <= q (two ballots: 32-ary search over pre1, then over pre)
@@ -496,6 +497,50 @@ __device__ __forceinline__ void run_parts(int t, int total, const int *__restric
             for (int u = 0; u < U; ++u)
                 if (c[u] >= 0) f(c[u], kNumeric ? av * v[u] : real(0));
         }
+    }
+    __syncthreads();
+}
+
+// Walk of the staged segments for classes whose B rows are SHORT (C = A * B with a few entries per row of B:
+// configs C4 / C5): a part -- up to 256 products of ONE B row -- would hold 4 products there and a warp would spend
+// its ~100 instructions of part bookkeeping on them.  Here the prefix of the staged segments counts products
+// (scan_parts<kFlat>), a warp takes 128 consecutive products of the slab, finds the entry of the first one with the
+// same two-ballot search and every lane advances through the entries on its own (the traversal of the hash classes,
+// for_each_product, on pre-cut segments).  Ends with a barrier.
+template <int BS, bool kNumeric, typename real, typename F>
+__device__ __forceinline__ void run_flat(int t, int total, const int *__restrict__ b_col, const real *__restrict__ b_val,
+                                         PartScratch<BS, real> &s, F &&f)
+{
+    constexpr int U = 4;
+    const int lane = t & 31;
+    for (int base_p = (t >> 5) * (32 * U); base_p < total; base_p += BS * U) {
+        int e = part_entry<BS, real>(s, base_p, lane);
+        int next = s.pre[e + 1];
+        int koff = s.kb[e] - s.pre[e];
+        real av = kNumeric ? s.av[e] : real(0);
+        int c[U];
+        real v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = base_p + u * 32 + lane;
+            c[u] = -1;
+            v[u] = real(0);
+            if (p < total) {
+                if (p >= next) {
+                    do {
+                        ++e;
+                        next = s.pre[e + 1];
+                    } while (p >= next);
+                    koff = s.kb[e] - s.pre[e];
+                    if (kNumeric) av = s.av[e];
+                }
+                c[u] = ld_nc(b_col + koff + p);
+                if (kNumeric) v[u] = av * ld_nc(b_val + koff + p);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (c[u] >= 0) f(c[u], v[u]);
     }
     __syncthreads();
 }

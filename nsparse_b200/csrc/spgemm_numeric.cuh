@@ -89,17 +89,19 @@ num_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                 const int *__restrict__ b_col, const real *__restrict__ b_val,
                 const long long *__restrict__ c_rpt, int *__restrict__ c_col, real *__restrict__ c_val,
                 const int *__restrict__ row_perm, int *__restrict__ bins, int bin_lo, int bin_hi,
-                int queue, int tmax, int sorted, const __grid_constant__ PeerOut peer)
+                int queue, int tmax, int sorted, int nb_max, int n_cols, const __grid_constant__ PeerOut peer)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NG = BS / GROUP;
     __shared__ FlatScratch<GROUP, real> s_flat[NG];
     __shared__ int s_row;
     __shared__ int s_fill[NG];
+    __shared__ int s_maxb[NG];
     const int g = threadIdx.x / GROUP, t = threadIdx.x % GROUP;
-    // values first (8-byte aligned for fp64), then keys
+    // values first (8-byte aligned for fp64), then keys, then the bucket counters of the output ordering
     real *vals = reinterpret_cast<real *>(smem_raw) + (size_t)g * tmax;
     int *keys = reinterpret_cast<int *>(smem_raw + sizeof(real) * (size_t)NG * tmax) + (size_t)g * tmax;
+    int *cnt = reinterpret_cast<int *>(smem_raw + (sizeof(real) + sizeof(int)) * (size_t)NG * tmax) + (size_t)g * nb_max;
     int lo, hi;
     class_range(bins, bin_lo, bin_hi, lo, hi);
     const int n = hi - lo;
@@ -131,10 +133,83 @@ num_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
         if (t == 0) s_fill[g] = 0;
         group_sync<GROUP>();
         if (sorted) {
-            bitonic_sort_slots<GROUP, real>(keys, vals, tsize, t);
-            for (int i = t; i < nnz; i += GROUP) {
-                c_col[off + i] = keys[i];
-                c_val[off + i] = vals[i];
+            // Output order by BUCKETS instead of sorting the table (round 1: bitonic sort of all tsize slots, ~100
+            // barrier-separated stages at 16384 slots -- 99 ms of the 165 ms of config C5 on 8 GPUs, 10.8 ms of C2):
+            // the column range is cut into nb <= tsize / 2 equal buckets, the row's keys are counted per bucket
+            // (shared-memory atomics), the counts are scanned, every (key, value) goes straight to C at its bucket's
+            // cursor, and the keys that share a bucket are ranked among themselves by counting.  Rows whose columns
+            // cluster into one bucket (more than kMaxBucket keys) fall back to the bitonic sort.
+            constexpr int kMaxBucket = 768;     // beyond this the O(bucket^2) ranking costs more than the bitonic sort
+            int nb = tsize >> 1;
+            if (nb > nb_max) nb = nb_max;
+            int shift = 0;
+            while (((unsigned)(n_cols - 1) >> shift) >= (unsigned)nb) ++shift;
+            for (int i = t; i < nb; i += GROUP) cnt[i] = 0;
+            if (t == 0) s_maxb[g] = 0;
+            group_sync<GROUP>();
+            for (int i = t; i < tsize; i += GROUP) {
+                const int key = keys[i];
+                if (key != kEmptyKey) atomicAdd(&cnt[(unsigned)key >> shift], 1);
+            }
+            group_sync<GROUP>();
+            // exclusive scan of the counters: thread t owns `per` consecutive buckets
+            const int per = nb >= GROUP ? nb / GROUP : 1;
+            const int b0 = t * per;
+            int sum = 0, mx = 0;
+            if (b0 < nb)
+                for (int k = 0; k < per; ++k) {
+                    const int c = cnt[b0 + k];
+                    sum += c;
+                    mx = c > mx ? c : mx;
+                }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if ((t & 31) == 0 && mx > 0) atomicMax(&s_maxb[g], mx);
+            const int inc = group_inclusive_scan<GROUP>(sum, t, s_flat[g].wtot);
+            group_sync<GROUP>();
+            if (s_maxb[g] > kMaxBucket) {
+                bitonic_sort_slots<GROUP, real>(keys, vals, tsize, t);
+                for (int i = t; i < nnz; i += GROUP) {
+                    c_col[off + i] = keys[i];
+                    c_val[off + i] = vals[i];
+                }
+            } else {
+                int run = inc - sum;
+                if (b0 < nb)
+                    for (int k = 0; k < per; ++k) {
+                        const int c = cnt[b0 + k];
+                        cnt[b0 + k] = run;          // cursor of the bucket
+                        run += c;
+                    }
+                group_sync<GROUP>();
+                for (int i = t; i < tsize; i += GROUP) {
+                    const int key = keys[i];
+                    if (key != kEmptyKey) {
+                        const int pos = atomicAdd(&cnt[(unsigned)key >> shift], 1);
+                        c_col[off + pos] = key;
+                        c_val[off + pos] = vals[i];
+                    }
+                }
+                group_sync<GROUP>();                // (the group's global writes are visible to the group)
+                // cnt[b] is now the END of bucket b.  Every entry finds its place inside its bucket by counting the
+                // smaller keys of the bucket (rank by counting, read back from C through L1 / L2) and goes to the -- now
+                // free -- table at that position; the ordered row is then copied out with coalesced stores.
+                for (int p = t; p < nnz; p += GROUP) {
+                    const int key = c_col[off + p];
+                    const real v = c_val[off + p];
+                    const unsigned bk = (unsigned)key >> shift;
+                    const int s0 = bk > 0 ? cnt[bk - 1] : 0;
+                    const int e0 = cnt[bk];
+                    int r = 0;
+                    for (int q = s0; q < e0; ++q) r += c_col[off + q] < key;
+                    keys[s0 + r] = key;
+                    vals[s0 + r] = v;
+                }
+                group_sync<GROUP>();
+                for (int i = t; i < nnz; i += GROUP) {
+                    c_col[off + i] = keys[i];
+                    c_val[off + i] = vals[i];
+                }
             }
         } else {
             // sort = false (cuda-cpp/inc/HashSpGEMM_volta.hpp:508-605, 1018-1031): the occupied slots are compacted in
@@ -194,7 +269,7 @@ __device__ __forceinline__ int select32(unsigned x, int n)
 // loops cost the single-GPU kernel 25 % -- register allocation of the hot loops).
 // kMulti: the instantiation for the rows with more than BS entries of A (red.global mode); the other one
 // skips them and vice versa -- two launches over the same class, so that neither carries the other's code.
-template <typename real, int BS, int kMode, bool kPeers, bool kMulti>
+template <typename real, int BS, int kMode, bool kPeers, bool kMulti, bool kFlat>
 __global__ void __launch_bounds__(BS, 1)
 num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                   const real *__restrict__ a_val, const int *__restrict__ b_rpt,
@@ -303,21 +378,31 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
             // ---- mark ----
             int staged_total = 0;
             const unsigned ncols = (unsigned)(c1 - c0);
+            auto mark_one = [&](int c, real) {                 // flat traversal: one bit per product
+                const unsigned cc = (unsigned)(c - c0);
+                atomicOr(bm32 + bitmap_word32(cc >> 5), 1u << (cc & 31u));
+            };
             if (one_slab) {
                 if (kSeg)
-                    staged_total = stage_window_seg<BS, true, real>(t, a_beg, E, a_val, seg, seg_stride, win, win == 0, s_part);
+                    staged_total = stage_window_seg<BS, true, real, kFlat>(t, a_beg, E, a_val, seg, seg_stride, win, win == 0, s_part);
                 else
-                    staged_total = stage_window<BS, true, real>(t, a_beg, E, glog, a_col, a_val, b_rpt, b_col, c1,
+                    staged_total = stage_window<BS, true, real, kFlat>(t, a_beg, E, glog, a_col, a_val, b_rpt, b_col, c1,
                                                                 win == 0 || !kSorted, cut_hi, s_part);
                 PH(1);
-                run_parts_mark<BS, !kSorted, real>(t, staged_total, b_col, b_vec_end, s_part, bm32, c0, ncols);
+                if (kFlat)
+                    run_flat<BS, false, real>(t, staged_total, b_col, b_val, s_part, mark_one);
+                else
+                    run_parts_mark<BS, !kSorted, real>(t, staged_total, b_col, b_vec_end, s_part, bm32, c0, ncols);
                 PH(2);
             } else {
                 for (int base = a_beg; base < a_end; base += BS) {
-                    const int total = kSeg ? stage_slab_seg<BS, false, real>(t, base, a_end, a_val, seg, seg_stride, win, s_part)
-                                           : stage_parts_range<BS, false, real>(t, base, a_end, a_col, a_val, b_rpt, b_col, c0,
+                    const int total = kSeg ? stage_slab_seg<BS, false, real, kFlat>(t, base, a_end, a_val, seg, seg_stride, win, s_part)
+                                           : stage_parts_range<BS, false, real, kFlat>(t, base, a_end, a_col, a_val, b_rpt, b_col, c0,
                                                                                 c1, cut_lo, cut_hi, s_part);
-                    run_parts_mark<BS, !kSorted, real>(t, total, b_col, b_vec_end, s_part, bm32, c0, ncols);
+                    if (kFlat)
+                        run_flat<BS, false, real>(t, total, b_col, b_val, s_part, mark_one);
+                    else
+                        run_parts_mark<BS, !kSorted, real>(t, total, b_col, b_vec_end, s_part, bm32, c0, ncols);
                     PH(2);
                 }
             }
@@ -433,18 +518,21 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                 };
                 int total = staged_total;                  // one chunk (or unsorted B): the mark pass staged it
                 if (kSeg && nch > 1)
-                    total = tab_ok ? stage_chunk_tab<BS, real>(t, E, k, s_part)
-                                   : stage_chunk_seg<BS, real>(t, a_beg, E, glog, b_col, seg, seg_stride, win, col_lo, col_hi,
+                    total = tab_ok ? stage_chunk_tab<BS, real, kFlat>(t, E, k, s_part)
+                                   : stage_chunk_seg<BS, real, kFlat>(t, a_beg, E, glog, b_col, seg, seg_stride, win, col_lo, col_hi,
                                                                k == 0, k == nch - 1, s_part);
                 else if (kSorted && nch > 1)
-                    total = stage_chunk<BS, real>(t, E, glog, b_col, col_hi, k == nch - 1, s_part);
+                    total = stage_chunk<BS, real, kFlat>(t, E, glog, b_col, col_hi, k == nch - 1, s_part);
                 else
                     __syncthreads();
                 PH(7);
                 // (a variant that issued the rank lookups, accumulator reads and compare-and-swaps of four products
                 // side by side instead of one LDS / FADD / ATOMS.CAST.SPIN chain per product measured 8 % SLOWER:
                 // profiles/r2_ab_value_pass_batched_cas_vs_spin_s20.txt)
-                run_parts<BS, true, real>(t, total, b_col, b_val, s_part, add);
+                if (kFlat)
+                    run_flat<BS, true, real>(t, total, b_col, b_val, s_part, add);
+                else
+                    run_parts<BS, true, real>(t, total, b_col, b_val, s_part, add);
                 PH(8);
                 real *cv = c_val + out + r0;
                 int *cc = c_col + out + r0;
@@ -507,10 +595,13 @@ num_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                 };
                 for (int base = a_beg; base < a_end; base += BS) {
                     // (the barriers of the staging order the zero fill before the adds)
-                    const int total = kSeg ? stage_slab_seg<BS, true, real>(t, base, a_end, a_val, seg, seg_stride, win, s_part)
-                                           : stage_parts_range<BS, true, real>(t, base, a_end, a_col, a_val, b_rpt, b_col, c0, c1,
+                    const int total = kSeg ? stage_slab_seg<BS, true, real, kFlat>(t, base, a_end, a_val, seg, seg_stride, win, s_part)
+                                           : stage_parts_range<BS, true, real, kFlat>(t, base, a_end, a_col, a_val, b_rpt, b_col, c0, c1,
                                                                                cut_lo, cut_hi, s_part);
-                    run_parts<BS, true, real>(t, total, b_col, b_val, s_part, add_red);
+                    if (kFlat)
+                        run_flat<BS, true, real>(t, total, b_col, b_val, s_part, add_red);
+                    else
+                        run_parts<BS, true, real>(t, total, b_col, b_val, s_part, add_red);
                     PH(10);
                 }
                 if (kPeers) {
@@ -574,16 +665,25 @@ static inline void num_prof_class(nsp_context *ctx, const char *name, int bin_lo
     a_rpt, a_col, a_val, b_rpt, b_col, b_val, c_rpt64, c_col, c_val, sp.d_row_perm, sp.d_bins
 
 template <typename real, int GROUP, int BS>
-static int launch_num_hash(nsp_context *ctx, const char *name, int grid, size_t smem, const int *a_rpt,
+static int launch_num_hash(nsp_context *ctx, const char *name, int grid, const int *a_rpt,
                            const int *a_col, const real *a_val, const int *b_rpt, const int *b_col,
                            const real *b_val, const long long *c_rpt64, int *c_col, real *c_val,
-                           int bin_lo, int bin_hi, int queue, int tmax)
+                           int bin_lo, int bin_hi, int queue, int tmax, int n_cols)
 {
     nsp_spgemm_state &sp = ctx->sp;
     auto kern = num_hash_kernel<real, GROUP, BS>;
+    constexpr int NG = BS / GROUP;
+    // table (values + keys) of every group, plus tmax / 2 bucket counters per group where the shared memory allows
+    // (the 1024-thread class in fp64 fills it: tmax / 4 there)
+    const size_t table = (size_t)tmax * (sizeof(real) + sizeof(int)) * NG;
+    const size_t limit = (size_t)ctx->max_smem_optin - (sizeof(FlatScratch<GROUP, real>) * NG + 256);
+    int nb_max = tmax / 2;
+    while (nb_max > 16 && table + (size_t)nb_max * sizeof(int) * NG > limit) nb_max >>= 1;
+    const size_t smem = table + (size_t)nb_max * sizeof(int) * NG;
     NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     num_prof_class(ctx, name, bin_lo, bin_hi);
-    kern<<<grid, BS, smem, ctx->stream>>>(NSP_NUM_ARGS, bin_lo, bin_hi, queue, tmax, ctx->opt_unsorted ? 0 : 1, ctx->peer_out);
+    kern<<<grid, BS, smem, ctx->stream>>>(NSP_NUM_ARGS, bin_lo, bin_hi, queue, tmax, ctx->opt_unsorted ? 0 : 1, nb_max, n_cols,
+                                          ctx->peer_out);
     ctx->prof_end();
     ctx->launches += 1;
     NSP_CUDA_TRY(ctx, cudaGetLastError());
@@ -604,12 +704,16 @@ static int preload_numeric_kernels(nsp_context *ctx)
     NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_hash_kernel<real, 32, 256>));
     NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_hash_kernel<real, 256, 256>));
     NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_hash_kernel<real, 1024, 1024>));
-    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 0, true, false>));
-    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 1, true, false>));
-    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 2, true, false>));
-    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 0, true, true>));
-    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 1, true, true>));
-    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 2, true, true>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 0, true, false, false>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 1, true, false, false>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 2, true, false, false>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 0, true, true, false>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 1, true, true, false>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 2, true, true, false>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 1, true, false, true>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 2, true, false, true>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 1, true, true, true>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 2, true, true, true>));
     ctx->peers_preloaded[which] = true;
     return 0;
 }
@@ -685,7 +789,6 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
     // bitonic sort of its table (n log^2 n): measured on R-MAT scale 20 (two windows) the bitmap wins above
     // ~2048 entries.  With many windows (very wide C) the hash ladder keeps everything it can hold.
     const long long nwin_host = ((long long)N + (1ll << wshift) - 1) >> wshift;
-    const int slot_bytes = 4 + (int)sizeof(real);
     int bm_bin = nwin_host <= 4 ? 8 : 10;
     if (ctx->opt_num_bitmap_min >= 0) {
         bm_bin = log_bin(num_imin(ctx->opt_num_bitmap_min, 0x7fffffff), kNumShift) + 1;
@@ -731,22 +834,37 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
         const int grid = num_imin(num_rows_in(sp, bm_bin, kNumBins - 1), (long long)(sms - push_sms));
         const long long a_entries = sp.a_nnz;
         const int mode = !sp.b_sorted ? 0 : (use_seg ? 2 : 1);
-        // [multi][peers][mode]
-        void (*kerns[2][2][3])(const int *, const int *, const real *, const int *, const int *, const real *,
-                               const long long *, int *, real *, const int *, int *, int, int, int, int, int, int, int,
-                               int, long long *, const int *, long long, const PeerOut) = {
-            {{num_bitmap_kernel<real, 1024, 0, false, false>, num_bitmap_kernel<real, 1024, 1, false, false>,
-              num_bitmap_kernel<real, 1024, 2, false, false>},
-             {num_bitmap_kernel<real, 1024, 0, true, false>, num_bitmap_kernel<real, 1024, 1, true, false>,
-              num_bitmap_kernel<real, 1024, 2, true, false>}},
-            {{num_bitmap_kernel<real, 1024, 0, false, true>, num_bitmap_kernel<real, 1024, 1, false, true>,
-              num_bitmap_kernel<real, 1024, 2, false, true>},
-             {num_bitmap_kernel<real, 1024, 0, true, true>, num_bitmap_kernel<real, 1024, 1, true, true>,
-              num_bitmap_kernel<real, 1024, 2, true, true>}}};
+        // flat traversal when the B rows of the class are short (spgemm_device.cuh run_flat): products per entry of A
+        // below 48 on average
+        long long cls_ip = 0, cls_len = 0;
+        for (int b = bm_bin; b < kNumBins; ++b) {
+            cls_ip += (long long)sp.h_binsum[kSumIp + b];
+            cls_len += (long long)sp.h_binsum[kSumLen + b];
+        }
+        const int flat = (mode != 0 && cls_len > 0 && cls_ip < 48 * cls_len && !ctx->opt_no_flat) || (mode != 0 && ctx->opt_no_flat < 0);
+        // [multi][peers][mode][flat]
+        using kern_t = void (*)(const int *, const int *, const real *, const int *, const int *, const real *, const long long *,
+                                int *, real *, const int *, int *, int, int, int, int, int, int, int, int, long long *,
+                                const int *, long long, const PeerOut);
+#define NSP_BM(mode_, peers_, multi_, flat_) num_bitmap_kernel<real, 1024, mode_, peers_, multi_, flat_>
+        static const kern_t kerns[2][2][3][2] = {
+            {{{NSP_BM(0, false, false, false), NSP_BM(0, false, false, false)},
+              {NSP_BM(1, false, false, false), NSP_BM(1, false, false, true)},
+              {NSP_BM(2, false, false, false), NSP_BM(2, false, false, true)}},
+             {{NSP_BM(0, true, false, false), NSP_BM(0, true, false, false)},
+              {NSP_BM(1, true, false, false), NSP_BM(1, true, false, true)},
+              {NSP_BM(2, true, false, false), NSP_BM(2, true, false, true)}}},
+            {{{NSP_BM(0, false, true, false), NSP_BM(0, false, true, false)},
+              {NSP_BM(1, false, true, false), NSP_BM(1, false, true, true)},
+              {NSP_BM(2, false, true, false), NSP_BM(2, false, true, true)}},
+             {{NSP_BM(0, true, true, false), NSP_BM(0, true, true, false)},
+              {NSP_BM(1, true, true, false), NSP_BM(1, true, true, true)},
+              {NSP_BM(2, true, true, false), NSP_BM(2, true, true, true)}}}};
+#undef NSP_BM
         // The long rows (few, each with millions of products: a tail of a handful of CTAs) go to a side stream
         // and start first; as their CTAs retire, the SMs pick up the CTAs of the main launch, whose dynamic row
         // queue balances whatever number of them is running.  Joined at the end of the phase.
-        auto kern = kerns[multi][peers ? 1 : 0][mode];
+        auto kern = kerns[multi][peers ? 1 : 0][mode][flat];
         NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaStream_t st = ctx->stream;
         if (multi && !ctx->opt_no_fork) {
@@ -775,25 +893,24 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
             const int hi = num_imin(9, bm_bin - 1);
             const int tmax = 16384;
             const int grid = num_imin(num_rows_in(sp, 8, hi), sms - push_sms);
-            if (launch_num_hash<real, 1024, 1024>(ctx, "num_hash_cta1024", grid, (size_t)tmax * slot_bytes, a_rpt,
-                                                  a_col, a_val, b_rpt, b_col, b_val, c_rpt64, c_col, c_val, 8, hi, 3,
-                                                  tmax) != 0)
+            if (launch_num_hash<real, 1024, 1024>(ctx, "num_hash_cta1024", grid, a_rpt, a_col, a_val, b_rpt, b_col, b_val,
+                                                  c_rpt64, c_col, c_val, 8, hi, 3, tmax, N) != 0)
                 return -1;
         }
         if (bm_bin > 5 && num_rows_in(sp, 5, num_imin(7, bm_bin - 1)) > 0) {
             const int hi = num_imin(7, bm_bin - 1);
             const int tmax = 4096;
             const int grid = num_imin(num_rows_in(sp, 5, hi), (long long)sms * 4);
-            if (launch_num_hash<real, 256, 256>(ctx, "num_hash_cta256", grid, (size_t)tmax * slot_bytes, a_rpt, a_col,
-                                                a_val, b_rpt, b_col, b_val, c_rpt64, c_col, c_val, 5, hi, 2, tmax) != 0)
+            if (launch_num_hash<real, 256, 256>(ctx, "num_hash_cta256", grid, a_rpt, a_col, a_val, b_rpt, b_col, b_val,
+                                                c_rpt64, c_col, c_val, 5, hi, 2, tmax, N) != 0)
                 return -1;
         }
         if (num_rows_in(sp, 1, num_imin(4, bm_bin - 1)) > 0) {
             const int hi = num_imin(4, bm_bin - 1);
             const int tmax = 512;
             const int grid = num_imin((num_rows_in(sp, 1, hi) + 7) / 8, (long long)sms * 4);
-            if (launch_num_hash<real, 32, 256>(ctx, "num_hash_warp", grid, (size_t)tmax * slot_bytes * 8, a_rpt, a_col,
-                                               a_val, b_rpt, b_col, b_val, c_rpt64, c_col, c_val, 1, hi, 1, tmax) != 0)
+            if (launch_num_hash<real, 32, 256>(ctx, "num_hash_warp", grid, a_rpt, a_col, a_val, b_rpt, b_col, b_val, c_rpt64,
+                                               c_col, c_val, 1, hi, 1, tmax, N) != 0)
                 return -1;
         }
         if (num_rows_in(sp, 0, 0) > 0) {

@@ -122,7 +122,7 @@ sym_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
 // is the popcount of the window, taken by the sweep that also clears it for the next row.  With more
 // than one window the sub-range of each B row is found by binary search, so a product is still read
 // exactly once.
-template <int BS, bool kSorted>
+template <int BS, bool kSorted, bool kFlat>
 __global__ void __launch_bounds__(BS, 1)
 sym_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
                   const int *__restrict__ b_rpt, const int *__restrict__ b_col,
@@ -157,10 +157,18 @@ sym_bitmap_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
             const int c0 = (int)((unsigned)win << wshift);
             const int c1 = (int)min((unsigned)N, (unsigned)c0 + W);
             for (int base = a_beg; base < a_end; base += BS) {
-                const int total = stage_parts_range<BS, false, float>(t, base, a_end, a_col, (const float *)nullptr,
-                                                                      b_rpt, b_col, c0, c1, kSorted && win > 0,
-                                                                      kSorted && win < nwin - 1, s_part);
-                run_parts_mark<BS, !kSorted, float>(t, total, b_col, b_vec_end, s_part, bm, c0, (unsigned)(c1 - c0));
+                const int total = stage_parts_range<BS, false, float, kFlat>(t, base, a_end, a_col, (const float *)nullptr,
+                                                                             b_rpt, b_col, c0, c1, kSorted && win > 0,
+                                                                             kSorted && win < nwin - 1, s_part);
+                if (kFlat) {
+                    // short B rows (products per entry of A below 48 on average): flat traversal, one bit per product
+                    run_flat<BS, false, float>(t, total, b_col, (const float *)nullptr, s_part, [&](int c, float) {
+                        const unsigned cc = (unsigned)(c - c0);
+                        atomicOr(bm + bitmap_word32(cc >> 5), 1u << (cc & 31u));
+                    });
+                } else {
+                    run_parts_mark<BS, !kSorted, float>(t, total, b_col, b_vec_end, s_part, bm, c0, (unsigned)(c1 - c0));
+                }
             }
             // count and clear in one sweep (run_parts ended with a barrier)
             for (int i = t; i < nw4; i += BS) {
@@ -259,7 +267,14 @@ int spgemm_symbolic(nsp_context *ctx, int M, int K, int N, const int *a_rpt, con
         if (rows_in(sp, bm_bin, kNumBins - 1) > 0) {
             const size_t smem = (size_t)1 << (wshift - 3);
             const int grid = imin(rows_in(sp, bm_bin, kNumBins - 1), (long long)sms);
-            auto kern = sp.b_sorted ? sym_bitmap_kernel<1024, true> : sym_bitmap_kernel<1024, false>;
+            long long cls_ip = 0, cls_len = 0;
+            for (int b = bm_bin; b < kNumBins; ++b) {
+                cls_ip += (long long)sp.h_binsum[kSumIp + b];
+                cls_len += (long long)sp.h_binsum[kSumLen + b];
+            }
+            const bool flat = sp.b_sorted && ((cls_len > 0 && cls_ip < 48 * cls_len && !ctx->opt_no_flat) || ctx->opt_no_flat < 0);
+            auto kern = !sp.b_sorted ? sym_bitmap_kernel<1024, false, false>
+                                     : (flat ? sym_bitmap_kernel<1024, true, true> : sym_bitmap_kernel<1024, true, false>);
             const int b_vec_end = ((reinterpret_cast<uintptr_t>(b_col) & 15u) != 0 || ctx->opt_no_vec)
                                       ? 0 : (int)(sp.b_nnz & ~3ll);
             NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -84,6 +84,53 @@ def partition_rows_by_measured(a_rpt, a_col, b_rpt, old_cuts, seconds, nparts: i
     return cuts, int(ip_prefix[-1])
 
 
+def partition_rows_minmax(a_rpt, a_col, b_rpt, c_rpt, old_cuts, seconds, nparts: int, bytes_per_entry: int,
+                          out_gbs: float = 450.0):
+    """Feedback cut that bounds BOTH what a rank computes and what it sends.  With the product gathered on every GPU a
+    rank's block costs max(compute, outbound transfer): compute as in partition_rows_by_measured (products at the rate
+    the row's old block was computed at), outbound = its entries of C * bytes_per_entry * (nparts - 1) at `out_gbs`
+    (what the copy engines of one B200 sustain towards 7 peers, profiles/r2_bench_c2_gpus8_*.json).  The cuts minimise
+    the largest of the two over all blocks (binary search on the bound, greedy blocks).  At 2 GPUs the compute bound is
+    the active one, at 8 the transfer: balancing compute alone left one GPU sending 118 GB of the 78 GB product
+    (2.1e9 of its entries to 7 peers) while another sent 22 GB."""
+    a_rpt = np.asarray(a_rpt, dtype=np.int64)
+    blen = np.diff(np.asarray(b_rpt, dtype=np.int64))
+    cs = np.concatenate([[0], np.cumsum(blen[np.asarray(a_col)])])
+    ip_prefix = cs[a_rpt].astype(np.float64)
+    M = len(a_rpt) - 1
+    comp = np.zeros(M + 1, dtype=np.float64)
+    for r in range(len(old_cuts) - 1):
+        lo, hi = old_cuts[r], old_cuts[r + 1]
+        ip_r = ip_prefix[hi] - ip_prefix[lo]
+        per_product = (seconds[r] / ip_r) if ip_r > 0 else 0.0
+        comp[lo + 1:hi + 1] = comp[lo] + (ip_prefix[lo + 1:hi + 1] - ip_prefix[lo]) * per_product
+    comm = np.asarray(c_rpt, dtype=np.float64) * (bytes_per_entry * max(nparts - 1, 0) / (out_gbs * 1e9))
+
+    def blocks_for(T):
+        cuts, start = [0], 0
+        while start < M and len(cuts) <= nparts:
+            e1 = int(np.searchsorted(comp, comp[start] + T, side="right")) - 1
+            e2 = int(np.searchsorted(comm, comm[start] + T, side="right")) - 1
+            end = max(min(e1, e2), start + 1)          # a single row always fits (it cannot be split)
+            cuts.append(min(end, M))
+            start = cuts[-1]
+        return cuts
+
+    lo_t, hi_t = 0.0, float(max(comp[-1], comm[-1])) + 1e-9
+    for _ in range(50):
+        mid = 0.5 * (lo_t + hi_t)
+        c = blocks_for(mid)
+        if c[-1] >= M and len(c) - 1 <= nparts:
+            hi_t = mid
+        else:
+            lo_t = mid
+    cuts = blocks_for(hi_t)
+    cuts = cuts[:nparts] + [M] if len(cuts) > nparts else cuts + [M] * (nparts + 1 - len(cuts))
+    for i in range(1, len(cuts)):
+        cuts[i] = min(max(cuts[i], cuts[i - 1]), M)
+    return cuts, int(ip_prefix[-1])
+
+
 def partition_rows_by_ip_device(a, b, nparts: int):
     """partition_rows_by_ip for matrices that live on the GPU (nsparse_b200.gen.DeviceCSR): the same cuts, computed
     with torch on the device.  Returns (cuts, total_ip)."""

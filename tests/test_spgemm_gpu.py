@@ -424,3 +424,46 @@ def test_tile_pusher_on_one_gpu(ns, dtype, offset, mode):
     assert torch.equal(pcol, col) and torch.equal(pval, val)
     assert int((pcol[:offset] != -7).sum()) == 0 and int((pcol[offset + nnz:] != -7).sum()) == 0
     ctx.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("opts", [{}, {"sym_window_shift": 16, "num_window_shift": 16, "num_cap": 256},
+                                  {"no_seg": 1, "sym_window_shift": 16, "num_window_shift": 16, "num_cap": 256}])
+def test_flat_traversal_of_the_heavy_kernels(ns, dtype, opts):
+    """The traversal the bitmap kernels use when the B rows of the class are short (run_flat, configs C4 / C5), forced
+    on (no_flat = -1) for inputs that take the part traversal by default: R-MAT A^2 with low class thresholds, one
+    window and several windows x chunks, with and without the precomputed segments; and a product with really short
+    B rows (4 per row) and a wide C where it is the default.  Bit-exact against the oracle."""
+    from nsparse_b200 import gen
+
+    ctx = ns.Context(0)
+    ctx.set_option("no_flat", -1)
+    ctx.set_option("sym_bitmap_min", 64)
+    ctx.set_option("num_bitmap_min", 64)
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    a = gen.rmat_csr(13, 16, seed=6, dtype=dtype, values="small_int")
+    a.memcpy()
+    c = ns.spgemm_kernel_hash(a, a, ctx)
+    ctx.sync()
+    want = oracle.spgemm(a.rpt, a.col, a.val, a.rpt, a.col, a.val, acc_double=True)
+    got = c.to_host()
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+    ctx.close()
+    # default choice on short B rows: long rows of A (up to 3000 entries) times 4 entries per row of B, N = 300000
+    ctx = ns.Context(0)
+    rng = np.random.default_rng(8)
+    lens = np.r_[rng.integers(1, 60, 400), [1500, 3000, 2600, 1024, 1025]]
+    K, N = 20000, 300000
+    rpt = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    col = np.concatenate([np.sort(rng.choice(K, n, replace=False)) for n in lens]).astype(np.int32)
+    a2 = ns.CSR(len(lens), K, rpt, col, rng.integers(1, 4, len(col)).astype(dtype))
+    b2 = gen.er_csr(K, N, 4, seed=5, dtype=dtype, values="ones")
+    a2.memcpy()
+    b2.memcpy()
+    c = ns.spgemm_kernel_hash(a2, b2, ctx)
+    ctx.sync()
+    want = oracle.spgemm(a2.rpt, a2.col, a2.val, b2.rpt, b2.col, b2.val, acc_double=True, n_cols=N)
+    got = c.to_host()
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+    ctx.close()
