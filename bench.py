@@ -768,7 +768,11 @@ def run_spmv(args, ctx, peak, peak_src):
     cpu_omp_s = time.perf_counter() - t1
     d = np.abs(hy - want)
     rel = float((d / np.maximum(np.abs(want), 1e-300)).max())
-    ok, msg = oracle.ans_check(hy, want)
+    # y_i = 4 x_i - (neighbours) cancels: |y_i| can be 1e-5 of its terms, so the tolerance is applied to the error
+    # relative to sum_j |a_ij| |x_j| (componentwise backward error); the plain relative error is reported next to it
+    scale = oracle.spmv_csr(lap.rpt, lap.col, np.abs(lap.val), np.abs(hx), parallel=True)
+    rel_scaled = float((d / np.maximum(scale, 1e-300)).max())
+    ok = rel_scaled <= 1e-12
     # end to end through the host-buffer entry point (x in, y out over PCIe every call)
     L = ctx.lib
     hxp = torch.from_numpy(hx).pin_memory()
@@ -790,7 +794,9 @@ def run_spmv(args, ctx, peak, peak_src):
             "c_size": c_size, "nnz_amb": nnz_amb,
             "conversion_s": conv_s, "conversion_first_call_s": conv_first_s, "launches": launches,
             "timing": "100 calls replayed from CUDA graphs of 10",
-            "parity": {"ok": bool(ok), "max_rel": rel, "tol": 1e-12, "against": "csr_kernel restated (oracle.c), full size"},
+            "parity": {"ok": bool(ok), "max_err_over_abs_row_sum": rel_scaled, "tol": 1e-12, "max_rel_to_y": rel,
+                       "against": "csr_kernel restated (oracle.c), full size; the error of y_i is measured against sum_j |a_ij||x_j| "
+                                  "(y_i itself cancels to 1e-5 of its terms on this matrix)"},
             "cpu_baseline": {"serial": {"value": 2.0 * lap.nnz / cpu_serial_s / 1e9, "unit": "GFLOPS", "cores": 1, "kind": "port",
                                         "sample": "whole matrix, csr_kernel (nsparse.cu:240-259)"},
                              "openmp": {"value": 2.0 * lap.nnz / cpu_omp_s / 1e9, "unit": "GFLOPS", "cores": oracle.num_threads(),
