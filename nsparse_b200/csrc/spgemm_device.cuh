@@ -294,6 +294,7 @@ __device__ __forceinline__ int stage_window(int t, int a_beg, int E, int glog, c
         }
         int res = hi;
         if (cut_hi) res = group_lower_bound(b_col, lo, hi, c1, glog, t & 31);
+        __syncwarp();      // every lane of the entry's group has read s.end[e] before its leader overwrites it (racecheck)
         if (e < E && (t & ((1 << glog) - 1)) == 0) {
             s.kb[e] = lo;
             s.len[e] = res - lo;
@@ -321,6 +322,7 @@ __device__ __forceinline__ int stage_chunk(int t, int E, int glog, const int *__
         }
         int res = hi;
         if (!last) res = group_lower_bound(b_col, lo, hi, col_hi, glog, t & 31);
+        __syncwarp();      // every lane of the entry's group has read s.cur[e] before its leader moves it (racecheck)
         if (e < E && (t & ((1 << glog) - 1)) == 0) {
             s.kb[e] = lo;
             s.len[e] = res - lo;

@@ -11,3 +11,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"sym_bitmap|num_bitmap|num_hash_kernel" -c 6 -o gpurun_out/${R}_prof_spgemm -f python scripts/explore_spgemm.py --scale 20 --steps 1 --skip-check > gpurun_out/${R}_ncu_spgemm.log 2>&1; echo "ncu spgemm rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"amb_spmv" -c 2 -o gpurun_out/${R}_prof_spmv -f python scripts/spmv_c3.py 4096 > gpurun_out/${R}_ncu_spmv.log 2>&1; echo "ncu spmv rc=$?"
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${R}_smoke.txt 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/${R}_smoke.txt
+# racecheck of the cursor-search staging after the __syncwarp fix (profiles/r2_sanitizer/)
+python scripts/make_sanitize_inputs.py /tmp > /dev/null 2>&1
+NSP_OPTIONS=sym_bitmap_min=64,num_bitmap_min=64,sym_window_shift=16,num_window_shift=16,num_cap=128,no_seg=1 timeout 600 compute-sanitizer --tool racecheck --print-limit 20 oracle/_ref/dump_spgemm_ours_s /tmp/sanitize_a_s.bin /tmp/sanitize_b_s.bin /tmp/san_recheck.bin 0 > gpurun_out/${R}_racecheck_forced_search_after_fix.log 2>&1; grep -E "RACECHECK SUMMARY|hazard" gpurun_out/${R}_racecheck_forced_search_after_fix.log | head -5
