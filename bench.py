@@ -397,6 +397,8 @@ def run_ours(args):
         ctx.set_option("push_sms", args.push_sms)
     if args.gather_tma:
         ctx.set_option("gather_tma", 1)
+    if args.gather_sm != 1:
+        ctx.set_option("gather_sm", args.gather_sm)
     if not wl["on_device"]:
         b.memcpy(local)                    # B (replicated); A is B for C2
     torch.cuda.synchronize()
@@ -451,7 +453,8 @@ def run_ours(args):
             allt = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
             dist.all_gather(allt, mine)
             secs = [float(x.item()) for x in allt]
-            cuts, _ = ns.partition_rows_minmax(a.rpt, a.col, b.rpt, c_rpt, cuts, secs, world, 4 + V, args.out_gbs)
+            cuts, _ = ns.partition_rows_minmax(a.rpt, a.col, b.rpt, c_rpt, cuts, secs, world, 4 + V, args.out_gbs,
+                                                 args.tail_gbs if (args.gather_sm and not args.gather_tma) else None)
             a_loc = ns.row_block(a, cuts[rank], cuts[rank + 1])
             a_loc.memcpy(local)
         c = None
@@ -478,6 +481,11 @@ def run_ours(args):
     ctx.profile(False)
     nnz_c, ip = c.nnz, total_ip
     per_rank = None
+    tiles_stats = (0, 0)
+    if world > 1 and peers is not None and peers.fused and not args.gather_tma:
+        n_ce, n_sm = C.c_longlong(0), C.c_longlong(0)
+        ctx.check(ctx.lib.nsp_spgemm_peers_stats(ctx.handle, C.byref(n_ce), C.byref(n_sm)))
+        tiles_stats = (n_ce.value, n_sm.value)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -573,7 +581,8 @@ def run_ours(args):
             gather.update(ms_no_gather=ms_ng, ms_gather_exposed=ms_step - ms_ng,
                           nvlink_out_bytes_per_gpu_max=out_b, nvlink_in_bytes_per_gpu_max=in_b,
                           nvlink_in_GBs_over_step=in_b / ms_step / 1e6, nvlink_out_GBs_over_step=out_b / ms_step / 1e6,
-                          nvlink_floor_ms=in_b / 700e9 * 1e3,
+                          nvlink_floor_ms=in_b / 700e9 * 1e3, tiles_by_copy_engines_rank0=tiles_stats[0],
+                          tiles_by_sm_stores_rank0=tiles_stats[1],
                           note="floor = inbound bytes at the 700 GB/s one GPU was measured to receive "
                                "(profiles/r1_probe_nvlink_multicast_2gpu.txt)")
 
@@ -643,7 +652,9 @@ def run_ours(args):
                       "own moves them into all peers with cp.async.bulk while the rest computes" if (args.gather == "fused" and args.gather_tma) else
                       "overlapped, copy engines: the heavy rows are computed tile by tile, the numeric kernels count finished entries "
                       "per tile, and the calling host thread hands every finished tile to cudaMemcpyAsync for each peer while the "
-                      "rest is computed (nsp_spgemm_set_peers)" if args.gather == "fused" else
+                      "rest is computed (nsp_spgemm_set_peers)" + ("; tiles still unsent when the kernels end are stored to all peers by "
+                      "an SM copy kernel next to the copy engines" if args.gather_sm == 1 else "; SM stores only, after the kernels"
+                      if args.gather_sm == 2 else "") if args.gather == "fused" else
                       f"pipelined: the block is computed in {args.pieces} pieces, the copy engines carry every finished piece")
         line = {
             "metric": "SpGEMM GFLOPS (C=A^2)" if wl["square"] else "SpGEMM GFLOPS (C=A*B)", "value": gflops, "unit": "GFLOPS",
@@ -660,7 +671,7 @@ def run_ours(args):
             line["config"]["partition"] = ("equal intermediate products" if (args.ip_partition or wl["on_device"]) else
                                            "feedback: a block costs max(compute, outbound transfer) -- rows charged their "
                                            "intermediate products at the rate their block was computed at in the previous warm-up "
-                                           f"product, entries of C at {args.out_gbs:.0f} GB/s to the N-1 peers (partition_rows_minmax; "
+                                           f"product, entries of C at {args.out_gbs:.0f} GB/s to the N-1 peers while the kernels run and {args.tail_gbs:.0f} GB/s after (partition_rows_minmax; "
                                            "repeated products on one pattern -- a one-shot call has the equal-products cut)")
         if gather is not None:
             line["gather"] = gather
@@ -828,7 +839,9 @@ def main():
     ap.add_argument("--push-sms", type=int, default=0, help="N > 1, --gather-tma: SMs of the pusher kernel (0: library default)")
     ap.add_argument("--gather-tma", action="store_true", help="N > 1: the TMA pusher kernel instead of the copy engines")
     ap.add_argument("--ip-partition", action="store_true", help="N > 1: keep the equal-intermediate-products row blocks")
-    ap.add_argument("--out-gbs", type=float, default=450.0, help="N > 1: outbound GB/s per GPU assumed by the row partition")
+    ap.add_argument("--gather-sm", type=int, default=1, help="N > 1: 1 = tiles left when the kernels end go out by SM stores next to the copy engines, 0 = copy engines only, 2 = SM stores only")
+    ap.add_argument("--out-gbs", type=float, default=400.0, help="N > 1: outbound GB/s per GPU (copy engines, while the kernels run) assumed by the row partition")
+    ap.add_argument("--tail-gbs", type=float, default=650.0, help="N > 1: outbound GB/s per GPU once the kernels have ended (copy engines + SM stores) assumed by the row partition")
     ap.add_argument("--nccl-gather", action="store_true", help="N > 1: gather C with NCCL broadcasts instead of peer stores")
     ap.add_argument("--no-check", action="store_true", help="N > 1: skip the gather_ok check")
     ap.add_argument("--no-e2e", action="store_true")

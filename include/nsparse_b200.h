@@ -178,14 +178,21 @@ int nsp_copy_async(nsp_context *ctx, void *d_dst, const void *d_src, size_t byte
  * entry of C it produces to d_peer_col[p] / d_peer_val[p] + elem_offset + (the same index) for p < npeers (at
  * most 7): the bases of the FULL C.col / C.val arrays of the other GPUs and the displacement of this rank's
  * row block in them (d_c_col / d_c_val passed to the numeric call must then be this rank's own full arrays
- * + elem_offset).  The block is cut into tiles of 8192 entries; the numeric kernels count finished entries
- * per tile, and a persistent pusher kernel on a few SMs of its own (option "push_sms", default 16) stores
- * every completed tile into all peers through the TMA (cp.async.bulk shared -> peer global) while the other
- * SMs keep computing.  The transfer is complete when the context's stream is.  npeers == 0 switches it off.
- * nsp_spgemm_peers_status synchronises and reports whether the pusher ever gave up waiting (it never should). */
+ * + elem_offset).  The block is cut into tiles of 2^20 .. 2^26 entries; the numeric kernels count finished
+ * entries per tile and raise a flag in host-mapped memory when a tile is complete; the calling host thread
+ * polls the flags while the kernels run and hands finished tiles to the copy engines (cudaMemcpyAsync, one
+ * stream per peer, a short queue); what is finished but not queued when the kernels end is stored to all
+ * peers by an SM copy kernel on the context's stream (option "gather_sm": 1 default, 0 copy engines only,
+ * 2 SM stores only).  Option "gather_tma" = 1 selects the persistent TMA pusher kernel instead (tiles of 4096
+ * entries, option "push_sms"; measured slower, kept as an option).  The transfer is complete when the
+ * context's stream is.  npeers == 0 switches it off.
+ * nsp_spgemm_peers_status synchronises and reports whether the pusher kernel ever gave up waiting (it never
+ * should); nsp_spgemm_peers_stats returns how many tiles of the last product left through the copy engines
+ * and through SM stores. */
 int nsp_spgemm_set_peers(nsp_context *ctx, int npeers, void *const *d_peer_col, void *const *d_peer_val,
                          long long elem_offset);
 int nsp_spgemm_peers_status(nsp_context *ctx, int *h_error);
+int nsp_spgemm_peers_stats(nsp_context *ctx, long long *h_copy_engine_tiles, long long *h_sm_tiles);
 int nsp_push_to_peers(nsp_context *ctx, int npeers, void *const *d_peer_bases, size_t byte_offset,
                       const void *d_src, size_t nbytes);
 

@@ -115,6 +115,7 @@ int nsp_set_option(nsp_context *ctx, const char *name, long long value)
     else if (!strcmp(name, "no_flat")) ctx->opt_no_flat = value;
     else if (!strcmp(name, "gather_tma")) ctx->opt_gather_tma = value;
     else if (!strcmp(name, "dma_tile_log")) ctx->opt_dma_tile_log = value;
+    else if (!strcmp(name, "gather_sm")) ctx->opt_gather_sm = value;
     else if (!strcmp(name, "sort")) ctx->opt_unsorted = value == 0;
     else if (!strcmp(name, "phase_timing")) {
         // value 1: start accumulating; value 2: print the totals (cycles summed over CTAs) and reset
@@ -238,6 +239,14 @@ int nsp_spgemm_set_peers(nsp_context *ctx, int npeers, void *const *d_peer_col, 
         po.val[p] = d_peer_val[p];
     }
     ctx->peer_out = po;
+    return 0;
+}
+
+int nsp_spgemm_peers_stats(nsp_context *ctx, long long *h_copy_engine_tiles, long long *h_sm_tiles)
+{
+    NSP_REQUIRE_CTX(ctx);
+    if (h_copy_engine_tiles) *h_copy_engine_tiles = ctx->dma.last_ce_tiles;
+    if (h_sm_tiles) *h_sm_tiles = ctx->dma.last_sm_tiles;
     return 0;
 }
 

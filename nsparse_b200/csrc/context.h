@@ -67,6 +67,12 @@ struct nsp_dma_push {
     size_t cap = 0;
     cudaStream_t copy_st[nsp::kMaxPeerOut] = {};
     cudaEvent_t ev_copy[nsp::kMaxPeerOut] = {};
+    // at most kSlots batches of copies are queued per peer (ev_slot: the end of each), so that what is left when the
+    // kernels end can go out through SM stores instead (ev_sm: the ends of those launches)
+    static constexpr int kSlots = 4, kSmSlots = 2;
+    cudaEvent_t ev_slot[nsp::kMaxPeerOut][kSlots] = {};
+    cudaEvent_t ev_sm[kSmSlots] = {};
+    long long last_ce_tiles = 0, last_sm_tiles = 0;   // of the last gather: tiles sent by copy engines / by SM stores
     char *d_sort = nullptr;                       // keys / values / temporary storage of order_rows_by_tile
     size_t sort_bytes = 0;
     bool active = false;
@@ -127,6 +133,8 @@ struct nsp_context {
     nsp_dma_push dma;
     long long opt_gather_tma = 0;        // 1: the TMA pusher kernel (peer_push.cu) instead of the copy engines
     long long opt_dma_tile_log = 0;      // > 0: log2 of the copy-engine tile (tests)
+    long long opt_gather_sm = 1;         // 1: tiles still unsent when the kernels end leave through SM stores next to
+                                         // the copy engines; 0: copy engines only; 2: SM stores only (tests)
     nsp::PeerOut last_push;  // the tile hand-off of the last product (diagnostics of nsp_spgemm_peers_status)
     // tile hand-off + pusher kernel of the multi-GPU allgatherv (peer_push.cu)
     cudaStream_t push_stream = nullptr;

@@ -14,10 +14,18 @@
 //       host-mapped memory; the host thread that called the numeric phase polls the flags while the kernels run
 //       and hands every finished tile to cudaMemcpyAsync, one stream per peer (peer_dma_drive).  The call returns
 //       when every tile has been issued; the context's stream then waits for the copy streams.
+//   (3) With many peers the block has to leave N-1 times and the copy engines of one GPU move ~0.4 TB/s in total
+//       (8 GPUs: profiles/r2_bench_c2_gpus8_compute_balanced.json), the whole GPU's SMs ~0.7 TB/s
+//       (profiles/r1_probe_nvlink_multicast_2gpu.txt) -- ~5 GB/s per SM, which is why a FEW SMs cannot do it.  So the
+//       copy-engine queue is kept short (kSlots batches per peer), and from the moment the numeric kernels have
+//       ended -- all SMs idle -- what is finished and not yet queued is stored to the peers by push_tiles_sm_kernel,
+//       which reads every piece once for all peers, while the copy engines keep draining their queue.
 #include <stdlib.h>
 
+#include <algorithm>
 #include <chrono>
 #include <thread>
+#include <vector>
 
 #include <cub/cub.cuh>
 
@@ -108,8 +116,12 @@ int peer_dma_reserve(nsp_context *ctx, long long ntiles, int npeers, int max_row
         if (!dp.copy_st[p]) {
             NSP_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&dp.copy_st[p], cudaStreamNonBlocking));
             NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&dp.ev_copy[p], cudaEventDisableTiming));
+            for (int k = 0; k < nsp_dma_push::kSlots; ++k)
+                NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&dp.ev_slot[p][k], cudaEventDisableTiming));
         }
     }
+    for (int k = 0; k < nsp_dma_push::kSmSlots; ++k)
+        if (!dp.ev_sm[k]) NSP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&dp.ev_sm[k], cudaEventDisableTiming));
     return 0;
 }
 
@@ -146,8 +158,67 @@ int peer_dma_begin(nsp_context *ctx, long long nnz_block)
     return 0;
 }
 
-// Polls the tile flags while the numeric kernels run and gives every finished tile to the copy engines; returns
-// when all tiles are issued (the context's stream then waits for the copies) or nothing moved for ten seconds.
+// [a, b) of the block's col and val arrays to every peer by SM stores: each 16-byte piece is loaded once and stored
+// to all peers (the copy engines read it once per peer).  Source and destinations are the same offsets of buffers
+// whose bases are 256-byte aligned, so one head / body / tail split serves all of them.
+struct PushPtrs {
+    char *col[kMaxPeerOut];
+    char *val[kMaxPeerOut];
+};
+
+template <int U>
+__device__ __forceinline__ void push_span(const char *__restrict__ src, char *const *dst, int np, size_t byte_lo, size_t nbytes,
+                                          size_t tid, size_t nth)
+{
+    const size_t mis = (16 - (byte_lo & 15)) & 15;
+    const size_t head = mis < nbytes ? mis : nbytes;
+    const size_t body = (nbytes - head) & ~size_t(15);
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src + byte_lo + head);
+    const size_t n16 = body / 16;
+    size_t i = tid;
+    // U loads in flight per thread before the first store leaves
+    for (; i + (U - 1) * nth < n16; i += U * nth) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w)
+                         : "l"(s4 + i + u * nth));
+        for (int p = 0; p < np; ++p) {
+            uint4 *d4 = reinterpret_cast<uint4 *>(dst[p] + byte_lo + head);
+#pragma unroll
+            for (int u = 0; u < U; ++u) d4[i + u * nth] = v[u];
+        }
+    }
+    for (; i < n16; i += nth) {
+        const uint4 v = s4[i];
+        for (int p = 0; p < np; ++p) reinterpret_cast<uint4 *>(dst[p] + byte_lo + head)[i] = v;
+    }
+    const size_t tail0 = head + body;
+    const size_t nsmall = head / 4 + (nbytes - tail0) / 4;
+    for (size_t k = tid; k < nsmall; k += nth) {
+        const size_t off = byte_lo + (k < head / 4 ? k * 4 : tail0 + (k - head / 4) * 4);
+        const unsigned v = *reinterpret_cast<const unsigned *>(src + off);
+        for (int p = 0; p < np; ++p) *reinterpret_cast<unsigned *>(dst[p] + off) = v;
+    }
+}
+
+__global__ void __launch_bounds__(512)
+push_tiles_sm_kernel(PushPtrs pp, int np, const char *__restrict__ col, const char *__restrict__ val, long long a, long long b,
+                     int val_bytes)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    push_span<4>(col, pp.col, np, (size_t)a * 4, (size_t)(b - a) * 4, tid, nth);
+    push_span<4>(val, pp.val, np, (size_t)a * val_bytes, (size_t)(b - a) * val_bytes, tid, nth);
+}
+
+// Polls the tile flags while the numeric kernels run and gives every finished tile to the copy engines, at most
+// kSlots batches queued per peer; once the kernels have ended, what is finished and not yet queued leaves through
+// push_tiles_sm_kernel on the context's stream, next to the copy engines.  (Measured on 8 x B200: seven peer streams
+// of copy-engine traffic leave one GPU at ~0.4 TB/s, SM stores at ~0.7 TB/s -- profiles/r1_probe_nvlink_multicast_2gpu.txt;
+// while the kernels run the SMs are not available, afterwards they are idle.)  Returns when all tiles are issued
+// (the context's stream then waits for the copies) or nothing moved for 20 s.
 int peer_dma_drive(nsp_context *ctx, const int *c_col_full, const void *c_val_full, int val_bytes)
 {
     nsp_dma_push &dp = ctx->dma;
@@ -162,39 +233,101 @@ int peer_dma_drive(nsp_context *ctx, const int *c_col_full, const void *c_val_fu
     // the copies ended -- the timeline of the overlap without a profiler
     const bool trace = getenv("NSP_DMA_TRACE") != nullptr;
     const auto t_begin = last;
-    std::vector<float> seen_ms;
+    std::vector<float> seen_ms((size_t)nt, -1.f);
     double kernels_done_ms = -1;
     auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(t - t_begin).count(); };
     volatile int *done = dp.h_done;
     const char *cv = static_cast<const char *>(c_val_full);
+    const size_t tile_bytes = ((size_t)1 << po.tile_log) * (size_t)(4 + val_bytes);
+    // a batch: up to 256 MB (copy engines) / 512 MB (SM stores) per peer
+    const int ce_run = (int)std::max<size_t>(1, ((size_t)256 << 20) / tile_bytes);
+    const int sm_run = (int)std::max<size_t>(1, ((size_t)512 << 20) / tile_bytes);
+    const int ce_slots = ctx->opt_gather_sm == 2 ? 0 : nsp_dma_push::kSlots;
+    const bool sm_ok = ctx->opt_gather_sm != 0;
+    int ce_head = 0, ce_inflight = 0, sm_head = 0, sm_inflight = 0;
+    bool kernels_done = false;
+    long long ce_tiles = 0, sm_tiles = 0;
+    PushPtrs pp;
+    for (int p = 0; p < po.n; ++p) {
+        pp.col[p] = reinterpret_cast<char *>(po.col[p]);
+        pp.val[p] = static_cast<char *>(po.val[p]);
+    }
     while (nsent < nt) {
+        // (before any SM launch of this call is queued behind them)
+        if (!kernels_done && cudaStreamQuery(ctx->stream) == cudaSuccess) {
+            kernels_done = true;
+            kernels_done_ms = ms_since(std::chrono::steady_clock::now());
+        }
+        // retire finished batches
+        while (ce_inflight > 0) {
+            const int slot = (ce_head - ce_inflight + 2 * nsp_dma_push::kSlots) % nsp_dma_push::kSlots;
+            bool fin = true;
+            for (int p = 0; p < po.n && fin; ++p) fin = cudaEventQuery(dp.ev_slot[p][slot]) == cudaSuccess;
+            if (!fin) break;
+            --ce_inflight;
+        }
+        while (sm_inflight > 0) {
+            const int slot = (sm_head - sm_inflight + 2 * nsp_dma_push::kSmSlots) % nsp_dma_push::kSmSlots;
+            if (cudaEventQuery(dp.ev_sm[slot]) != cudaSuccess) break;
+            --sm_inflight;
+        }
         bool any = false;
         for (int t = first; t < nt; ++t) {
             if (sent[t] || !done[t]) continue;
-            // a run of adjacent finished tiles goes out as one copy per peer and array
+            const bool by_ce = ce_inflight < ce_slots;
+            const bool by_sm = !by_ce && kernels_done && (sm_ok || ce_slots == 0) && sm_inflight < nsp_dma_push::kSmSlots;
+            if (!by_ce && !by_sm) break;
+            // a run of adjacent finished tiles goes out as one batch
+            const int run = by_ce ? ce_run : sm_run;
             int t1 = t;
-            while (t1 + 1 < nt && !sent[t1 + 1] && done[t1 + 1]) ++t1;
+            while (t1 + 1 < nt && t1 + 1 - t < run && !sent[t1 + 1] && done[t1 + 1]) ++t1;
             const long long lo = (po.tile0 + t) << po.tile_log, hi = (po.tile0 + t1 + 1) << po.tile_log;
             const long long a = lo > po.off ? lo : po.off, b = hi < po.off + po.nnz ? hi : po.off + po.nnz;
-            for (int p = 0; p < po.n; ++p) {
-                NSP_CUDA_TRY(ctx, cudaMemcpyAsync(po.col[p] + a, c_col_full + a, sizeof(int) * (size_t)(b - a), cudaMemcpyDeviceToDevice,
-                                                  dp.copy_st[p]));
-                NSP_CUDA_TRY(ctx, cudaMemcpyAsync(static_cast<char *>(po.val[p]) + (size_t)a * val_bytes, cv + (size_t)a * val_bytes,
-                                                  (size_t)val_bytes * (size_t)(b - a), cudaMemcpyDeviceToDevice, dp.copy_st[p]));
+            if (by_ce) {
+                const int slot = ce_head % nsp_dma_push::kSlots;
+                for (int p = 0; p < po.n; ++p) {
+                    NSP_CUDA_TRY(ctx, cudaMemcpyAsync(po.col[p] + a, c_col_full + a, sizeof(int) * (size_t)(b - a), cudaMemcpyDeviceToDevice,
+                                                      dp.copy_st[p]));
+                    NSP_CUDA_TRY(ctx, cudaMemcpyAsync(static_cast<char *>(po.val[p]) + (size_t)a * val_bytes, cv + (size_t)a * val_bytes,
+                                                      (size_t)val_bytes * (size_t)(b - a), cudaMemcpyDeviceToDevice, dp.copy_st[p]));
+                    NSP_CUDA_TRY(ctx, cudaEventRecord(dp.ev_slot[p][slot], dp.copy_st[p]));
+                }
+                ce_head = (ce_head + 1) % nsp_dma_push::kSlots;
+                ++ce_inflight;
+                ce_tiles += t1 - t + 1;
+            } else {
+                const int slot = sm_head % nsp_dma_push::kSmSlots;
+                push_tiles_sm_kernel<<<ctx->sm_count * 4, 512, 0, ctx->stream>>>(pp, po.n, reinterpret_cast<const char *>(c_col_full), cv, a, b,
+                                                                                  val_bytes);
+                {
+                    // (the queries above may have left cudaErrorNotReady behind: not an error)
+                    const cudaError_t e = cudaGetLastError();
+                    if (e != cudaSuccess && e != cudaErrorNotReady) NSP_CUDA_TRY(ctx, e);
+                }
+                NSP_CUDA_TRY(ctx, cudaEventRecord(dp.ev_sm[slot], ctx->stream));
+                ctx->launches += 1;
+                sm_head = (sm_head + 1) % nsp_dma_push::kSmSlots;
+                ++sm_inflight;
+                sm_tiles += t1 - t + 1;
             }
             for (int k = t; k <= t1; ++k) sent[k] = 1;
             nsent += t1 - t + 1;
-            if (trace)
-                for (int k = t; k <= t1; ++k) seen_ms.push_back((float)ms_since(std::chrono::steady_clock::now()));
             any = true;
             t = t1;
         }
+        if (trace) {
+            float now = -1.f;
+            for (int t = first; t < nt; ++t)
+                if (seen_ms[t] < 0 && done[t]) {
+                    if (now < 0) now = (float)ms_since(std::chrono::steady_clock::now());
+                    seen_ms[t] = now;
+                }
+        }
         while (first < nt && sent[first]) ++first;
-        if (trace && kernels_done_ms < 0 && cudaStreamQuery(ctx->stream) == cudaSuccess) kernels_done_ms = ms_since(std::chrono::steady_clock::now());
         if (any) {
             last = std::chrono::steady_clock::now();
         } else {
-            if (cudaStreamQuery(ctx->stream) == cudaSuccess && std::chrono::steady_clock::now() - last > std::chrono::seconds(1)) {
+            if (kernels_done && ce_inflight == 0 && sm_inflight == 0 && std::chrono::steady_clock::now() - last > std::chrono::seconds(1)) {
                 // every kernel of the product has finished and flags are still missing: an accounting error
                 bool missing = false;
                 for (int t = first; t < nt; ++t) missing = missing || (!sent[t] && !done[t]);
@@ -206,23 +339,31 @@ int peer_dma_drive(nsp_context *ctx, const int *c_col_full, const void *c_val_fu
             std::this_thread::yield();
         }
     }
+    dp.last_ce_tiles = ce_tiles;
+    dp.last_sm_tiles = sm_tiles;
+    {
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess && e != cudaErrorNotReady) NSP_CUDA_TRY(ctx, e);
+    }
     for (int p = 0; p < po.n; ++p) {
         NSP_CUDA_TRY(ctx, cudaEventRecord(dp.ev_copy[p], dp.copy_st[p]));
         NSP_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, dp.ev_copy[p], 0));
     }
-    if (trace && !seen_ms.empty()) {
+    if (trace && nt > 0) {
         const double issued_ms = ms_since(std::chrono::steady_clock::now());
-        if (kernels_done_ms < 0) {
-            // (the stream now also waits for the copies: time the kernels by the last flag instead)
-            kernels_done_ms = seen_ms.back();
-        }
+        std::vector<float> sm(seen_ms);
+        std::sort(sm.begin(), sm.end());
+        if (kernels_done_ms < 0) kernels_done_ms = sm.back();   // (the stream now also waits for the copies)
         for (int p = 0; p < po.n; ++p) cudaStreamSynchronize(dp.copy_st[p]);
         const double copies_ms = ms_since(std::chrono::steady_clock::now());
-        const size_t n = seen_ms.size();
-        fprintf(stderr, "[nsp dma] dev %d: %d tiles of 2^%d entries; flags seen at %.1f / %.1f / %.1f / %.1f / %.1f ms (first, 25%%, 50%%, 75%%, "
-                        "last); kernels done %.1f ms; all copies issued %.1f ms, landed %.1f ms\n",
-                ctx->device, nt, po.tile_log, seen_ms[0], seen_ms[n / 4], seen_ms[n / 2], seen_ms[3 * n / 4], seen_ms[n - 1], kernels_done_ms,
-                issued_ms, copies_ms);
+        cudaStreamSynchronize(ctx->stream);
+        const double all_ms = ms_since(std::chrono::steady_clock::now());
+        const size_t n = sm.size();
+        fprintf(stderr, "[nsp dma] dev %d: %d tiles of 2^%d entries (%lld by copy engines, %lld by SM stores); flags seen at %.1f / %.1f / "
+                        "%.1f / %.1f / %.1f ms (first, 25%%, 50%%, 75%%, last); kernels done %.1f ms; all issued %.1f ms, copy engines "
+                        "done %.1f ms, everything %.1f ms\n",
+                ctx->device, nt, po.tile_log, ce_tiles, sm_tiles, sm[0], sm[n / 4], sm[n / 2], sm[3 * n / 4], sm[n - 1], kernels_done_ms,
+                issued_ms, copies_ms, all_ms);
     }
     return 0;
 }
@@ -235,8 +376,11 @@ void peer_dma_destroy(nsp_context *ctx)
             cudaStreamSynchronize(dp.copy_st[p]);
             cudaStreamDestroy(dp.copy_st[p]);
             cudaEventDestroy(dp.ev_copy[p]);
+            for (int k = 0; k < nsp_dma_push::kSlots; ++k) cudaEventDestroy(dp.ev_slot[p][k]);
         }
     }
+    for (int k = 0; k < nsp_dma_push::kSmSlots; ++k)
+        if (dp.ev_sm[k]) cudaEventDestroy(dp.ev_sm[k]);
     cudaFree(dp.d_tile_cnt);
     if (dp.h_done) cudaFreeHost(dp.h_done);
     cudaFree(dp.d_sort);

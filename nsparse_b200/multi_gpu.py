@@ -85,14 +85,16 @@ def partition_rows_by_measured(a_rpt, a_col, b_rpt, old_cuts, seconds, nparts: i
 
 
 def partition_rows_minmax(a_rpt, a_col, b_rpt, c_rpt, old_cuts, seconds, nparts: int, bytes_per_entry: int,
-                          out_gbs: float = 450.0):
+                          out_gbs: float = 400.0, tail_gbs: float | None = None):
     """Feedback cut that bounds BOTH what a rank computes and what it sends.  With the product gathered on every GPU a
-    rank's block costs max(compute, outbound transfer): compute as in partition_rows_by_measured (products at the rate
-    the row's old block was computed at), outbound = its entries of C * bytes_per_entry * (nparts - 1) at `out_gbs`
-    (what the copy engines of one B200 sustain towards 7 peers, profiles/r2_bench_c2_gpus8_*.json).  The cuts minimise
-    the largest of the two over all blocks (binary search on the bound, greedy blocks).  At 2 GPUs the compute bound is
-    the active one, at 8 the transfer: balancing compute alone left one GPU sending 118 GB of the 78 GB product
-    (2.1e9 of its entries to 7 peers) while another sent 22 GB."""
+    rank's block costs its compute time -- as in partition_rows_by_measured: products at the rate the row's old block
+    was computed at -- plus whatever of its outbound transfer (its entries of C * bytes_per_entry * (nparts - 1)) is
+    left when the kernels end: `out_gbs` leave while they run (what the copy engines of one B200 sustain towards 7
+    peers, profiles/r2_bench_c2_gpus8_*.json), the rest at `tail_gbs` (copy engines and SM stores together,
+    csrc/peer_dma.cu; None: the copy engines alone, i.e. max(compute, transfer)).  The cuts minimise the largest cost
+    over all blocks (binary search on the bound, greedy blocks).  At 2 GPUs the compute is the active bound, at 8 the
+    transfer: balancing compute alone left one GPU sending 118 GB of the 78 GB product (2.1e9 of its entries to 7
+    peers) while another sent 22 GB."""
     a_rpt = np.asarray(a_rpt, dtype=np.int64)
     blen = np.diff(np.asarray(b_rpt, dtype=np.int64))
     cs = np.concatenate([[0], np.cumsum(blen[np.asarray(a_col)])])
@@ -104,19 +106,28 @@ def partition_rows_minmax(a_rpt, a_col, b_rpt, c_rpt, old_cuts, seconds, nparts:
         ip_r = ip_prefix[hi] - ip_prefix[lo]
         per_product = (seconds[r] / ip_r) if ip_r > 0 else 0.0
         comp[lo + 1:hi + 1] = comp[lo] + (ip_prefix[lo + 1:hi + 1] - ip_prefix[lo]) * per_product
-    comm = np.asarray(c_rpt, dtype=np.float64) * (bytes_per_entry * max(nparts - 1, 0) / (out_gbs * 1e9))
+    out_bytes = np.asarray(c_rpt, dtype=np.float64) * (bytes_per_entry * max(nparts - 1, 0))
+    during, after = out_gbs * 1e9, (tail_gbs if tail_gbs else out_gbs) * 1e9
+
+    def cost(start, end):
+        t = comp[end] - comp[start]
+        return t + max(0.0, out_bytes[end] - out_bytes[start] - during * t) / after
 
     def blocks_for(T):
         cuts, start = [0], 0
         while start < M and len(cuts) <= nparts:
-            e1 = int(np.searchsorted(comp, comp[start] + T, side="right")) - 1
-            e2 = int(np.searchsorted(comm, comm[start] + T, side="right")) - 1
-            end = max(min(e1, e2), start + 1)          # a single row always fits (it cannot be split)
-            cuts.append(min(end, M))
-            start = cuts[-1]
+            lo, hi = start + 1, M                      # a single row always fits (it cannot be split)
+            while lo < hi:
+                mid = (lo + hi + 1) // 2
+                if cost(start, mid) <= T:
+                    lo = mid
+                else:
+                    hi = mid - 1
+            cuts.append(lo)
+            start = lo
         return cuts
 
-    lo_t, hi_t = 0.0, float(max(comp[-1], comm[-1])) + 1e-9
+    lo_t, hi_t = 0.0, cost(0, M) + 1e-9
     for _ in range(50):
         mid = 0.5 * (lo_t + hi_t)
         c = blocks_for(mid)

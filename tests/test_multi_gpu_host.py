@@ -140,6 +140,43 @@ def test_partition_by_measured_times():
     assert 0.2 < share0_old < 0.3 and share0_new < 0.75 * share0_old
 
 
+def test_partition_minmax_bounds_compute_and_transfer():
+    """partition_rows_minmax: with a fast link the cut balances the measured compute, with a slow link the entries of
+    C every rank has to send; the largest block cost is never above that of the equal-products cut, with and without
+    the faster tail (SM stores once the kernels have ended); cuts are monotone and cover all rows."""
+    import numpy as np
+
+    import nsparse_b200 as ns
+    from nsparse_b200 import gen
+    from oracle import oracle
+
+    a = gen.rmat_csr(11, 16, seed=5, dtype=np.float32)
+    c_rpt = oracle.spgemm(a.rpt, a.col, a.val, a.rpt, a.col, a.val)[0].astype(np.int64)
+    n = 4
+    cuts, ip = ns.partition_rows_by_ip(a.rpt, a.col, a.rpt, n)
+    secs = [1e-3] * n
+    blen = np.diff(a.rpt).astype(np.int64)
+    ipp = np.concatenate([[0], np.cumsum(blen[a.col])])[a.rpt].astype(np.float64)
+
+    def worst(cs, out_gbs, tail_gbs):
+        w = 0.0
+        for r in range(n):
+            t = (ipp[cs[r + 1]] - ipp[cs[r]]) / ip * n * 1e-3
+            ob = float(c_rpt[cs[r + 1]] - c_rpt[cs[r]]) * 8 * (n - 1)
+            w = max(w, t + max(0.0, ob - out_gbs * 1e9 * t) / ((tail_gbs or out_gbs) * 1e9))
+        return w
+
+    for out_gbs, tail in ((1e6, None), (1e-3, None), (1e-3, 2e-3), (0.05, None), (0.05, 0.1)):
+        new, ip2 = ns.partition_rows_minmax(a.rpt, a.col, a.rpt, c_rpt, cuts, secs, n, 8, out_gbs, tail)
+        assert ip2 == ip and new[0] == 0 and new[-1] == a.M and all(x <= y for x, y in zip(new, new[1:]))
+        assert worst(new, out_gbs, tail) <= worst(cuts, out_gbs, tail) * (1 + 1e-9)
+        if out_gbs == 1e6:      # compute only: the equal-products cut again (a row either way)
+            assert all(abs(x - y) <= 1 for x, y in zip(new, cuts))
+        if out_gbs == 1e-3:     # transfer only: equal entries of C per rank, within the heaviest row
+            per = np.diff(c_rpt[new])
+            assert per.max() - per.min() <= 2 * np.diff(c_rpt).max() + 1
+
+
 def test_device_partition_and_generators_on_cpu_tensors():
     """The torch versions used for the full-size C4 / C5 inputs (nsparse_b200.gen.*_device, partition_rows_by_ip_device)
     are plain torch: on CPU tensors they must reproduce the numpy / native results bit for bit."""

@@ -384,12 +384,14 @@ def test_host_drain_fold(ns, ctx):
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("offset", [0, 12345])
-@pytest.mark.parametrize("mode", ["dma", "dma_small_tiles", "tma"])
+@pytest.mark.parametrize("mode", ["dma", "dma_small_tiles", "dma_small_tiles_3peers", "ce_only", "sm_only", "sm_only_small_tiles",
+                                  "sm_only_3peers", "tma"])
 def test_tile_pusher_on_one_gpu(ns, dtype, offset, mode):
     """The multi-GPU allgatherv path (tile counters in every numeric kernel, then either the copy engines driven by
-    the polling host thread, csrc/peer_dma.cu, or the TMA pusher kernel, csrc/peer_push.cu) with the 'peer' being a
-    second buffer on the SAME GPU: after the product the peer copy must equal C entry for entry at the block's
-    displacement, and nothing outside the block may have been touched."""
+    the polling host thread plus SM stores for what is left when the kernels end, csrc/peer_dma.cu -- each of the two
+    alone as well -- or the TMA pusher kernel, csrc/peer_push.cu) with the 'peer' being a second buffer on the SAME
+    GPU: after the product the peer copy must equal C entry for entry at the block's displacement, and nothing
+    outside the block may have been touched."""
     import ctypes as C
 
     import torch
@@ -399,8 +401,12 @@ def test_tile_pusher_on_one_gpu(ns, dtype, offset, mode):
     ctx = ns.Context(0)
     if mode == "tma":
         ctx.set_option("gather_tma", 1)
-    if mode == "dma_small_tiles":
+    if "small_tiles" in mode:
         ctx.set_option("dma_tile_log", 12)
+    if mode == "ce_only":
+        ctx.set_option("gather_sm", 0)
+    if mode.startswith("sm_only"):
+        ctx.set_option("gather_sm", 2)
     a = gen.rmat_csr(13, 16, seed=4, dtype=dtype, values="small_int")
     a.memcpy()
     d_rpt64, nnz, _ = ns.spgemm_symbolic(a, a, ctx)
@@ -408,9 +414,11 @@ def test_tile_pusher_on_one_gpu(ns, dtype, offset, mode):
     total = offset + nnz + 999
     col = torch.full((total,), -7, dtype=torch.int32, device="cuda")
     val = torch.full((total,), -7, dtype=tdt, device="cuda")
-    pcol = torch.full((total,), -7, dtype=torch.int32, device="cuda")
-    pval = torch.full((total,), -7, dtype=tdt, device="cuda")
-    ctx.check(ctx.lib.nsp_spgemm_set_peers(ctx.handle, 1, (C.c_void_p * 1)(pcol.data_ptr()), (C.c_void_p * 1)(pval.data_ptr()), offset))
+    npeers = 3 if mode.endswith("3peers") else 1
+    pcols = [torch.full((total,), -7, dtype=torch.int32, device="cuda") for _ in range(npeers)]
+    pvals = [torch.full((total,), -7, dtype=tdt, device="cuda") for _ in range(npeers)]
+    ctx.check(ctx.lib.nsp_spgemm_set_peers(ctx.handle, npeers, (C.c_void_p * npeers)(*[t.data_ptr() for t in pcols]),
+                                           (C.c_void_p * npeers)(*[t.data_ptr() for t in pvals]), offset))
     try:
         ns.spgemm_numeric(a, a, d_rpt64, nnz, ctx, out=(col[offset:], val[offset:]))
     finally:
@@ -421,8 +429,17 @@ def test_tile_pusher_on_one_gpu(ns, dtype, offset, mode):
     want = oracle.spgemm(a.rpt, a.col, a.val, a.rpt, a.col, a.val, acc_double=True)
     assert np.array_equal(col[offset:offset + nnz].cpu().numpy(), want[1])
     assert np.array_equal(val[offset:offset + nnz].cpu().numpy(), want[2])
-    assert torch.equal(pcol, col) and torch.equal(pval, val)
-    assert int((pcol[:offset] != -7).sum()) == 0 and int((pcol[offset + nnz:] != -7).sum()) == 0
+    for pcol, pval in zip(pcols, pvals):
+        assert torch.equal(pcol, col) and torch.equal(pval, val)
+        assert int((pcol[:offset] != -7).sum()) == 0 and int((pcol[offset + nnz:] != -7).sum()) == 0
+    if mode != "tma":
+        n_ce, n_sm = C.c_longlong(-1), C.c_longlong(-1)
+        ctx.check(ctx.lib.nsp_spgemm_peers_stats(ctx.handle, C.byref(n_ce), C.byref(n_sm)))
+        assert n_ce.value >= 0 and n_sm.value >= 0 and n_ce.value + n_sm.value > 0
+        if mode == "ce_only":
+            assert n_sm.value == 0
+        if mode.startswith("sm_only"):
+            assert n_ce.value == 0
     ctx.close()
 
 
