@@ -188,11 +188,12 @@ int nsp_copy_async(nsp_context *ctx, void *d_dst, const void *d_src, size_t byte
  * context's stream is.  npeers == 0 switches it off.
  * nsp_spgemm_peers_status synchronises and reports whether the pusher kernel ever gave up waiting (it never
  * should); nsp_spgemm_peers_stats returns how many tiles of the last product left through the copy engines
- * and through SM stores. */
+ * and through SM stores, and the time from the entry of the numeric call to the end of its kernels (what the
+ * rank needed for its own block, the input of the feedback row partition). */
 int nsp_spgemm_set_peers(nsp_context *ctx, int npeers, void *const *d_peer_col, void *const *d_peer_val,
                          long long elem_offset);
 int nsp_spgemm_peers_status(nsp_context *ctx, int *h_error);
-int nsp_spgemm_peers_stats(nsp_context *ctx, long long *h_copy_engine_tiles, long long *h_sm_tiles);
+int nsp_spgemm_peers_stats(nsp_context *ctx, long long *h_copy_engine_tiles, long long *h_sm_tiles, double *h_kernel_ms);
 int nsp_push_to_peers(nsp_context *ctx, int npeers, void *const *d_peer_bases, size_t byte_offset,
                       const void *d_src, size_t nbytes);
 

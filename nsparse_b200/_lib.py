@@ -79,7 +79,7 @@ SIGNATURES = {
     "nsp_copy_async": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
     "nsp_spgemm_set_peers": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), ll]),
     "nsp_spgemm_peers_status": (C.c_int, [vp, C.POINTER(C.c_int)]),
-    "nsp_spgemm_peers_stats": (C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "nsp_spgemm_peers_stats": (C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
     "nsp_mgpu_create": (C.c_int, [C.POINTER(vp), C.c_int, vp]),
     "nsp_mgpu_destroy": (C.c_int, [vp]),
     "nsp_mgpu_last_error": (C.c_char_p, [vp]),

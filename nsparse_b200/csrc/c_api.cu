@@ -242,11 +242,12 @@ int nsp_spgemm_set_peers(nsp_context *ctx, int npeers, void *const *d_peer_col, 
     return 0;
 }
 
-int nsp_spgemm_peers_stats(nsp_context *ctx, long long *h_copy_engine_tiles, long long *h_sm_tiles)
+int nsp_spgemm_peers_stats(nsp_context *ctx, long long *h_copy_engine_tiles, long long *h_sm_tiles, double *h_kernel_ms)
 {
     NSP_REQUIRE_CTX(ctx);
     if (h_copy_engine_tiles) *h_copy_engine_tiles = ctx->dma.last_ce_tiles;
     if (h_sm_tiles) *h_sm_tiles = ctx->dma.last_sm_tiles;
+    if (h_kernel_ms) *h_kernel_ms = ctx->dma.last_kernel_ms;
     return 0;
 }
 

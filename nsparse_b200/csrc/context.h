@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <chrono>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -73,6 +74,8 @@ struct nsp_dma_push {
     cudaEvent_t ev_slot[nsp::kMaxPeerOut][kSlots] = {};
     cudaEvent_t ev_sm[kSmSlots] = {};
     long long last_ce_tiles = 0, last_sm_tiles = 0;   // of the last gather: tiles sent by copy engines / by SM stores
+    std::chrono::steady_clock::time_point t_numeric;  // entry of the numeric phase
+    double last_kernel_ms = 0;                        // from there to the end of its kernels, as seen by the polling thread
     char *d_sort = nullptr;                       // keys / values / temporary storage of order_rows_by_tile
     size_t sort_bytes = 0;
     bool active = false;

@@ -256,7 +256,9 @@ int peer_dma_drive(nsp_context *ctx, const int *c_col_full, const void *c_val_fu
         // (before any SM launch of this call is queued behind them)
         if (!kernels_done && cudaStreamQuery(ctx->stream) == cudaSuccess) {
             kernels_done = true;
-            kernels_done_ms = ms_since(std::chrono::steady_clock::now());
+            const auto now = std::chrono::steady_clock::now();
+            kernels_done_ms = ms_since(now);
+            dp.last_kernel_ms = std::chrono::duration<double, std::milli>(now - dp.t_numeric).count();
         }
         // retire finished batches
         while (ce_inflight > 0) {
@@ -341,6 +343,8 @@ int peer_dma_drive(nsp_context *ctx, const int *c_col_full, const void *c_val_fu
     }
     dp.last_ce_tiles = ce_tiles;
     dp.last_sm_tiles = sm_tiles;
+    // (the last tile went to the copy engines the moment its flag came up: the kernels end about now)
+    if (!kernels_done) dp.last_kernel_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - dp.t_numeric).count();
     {
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess && e != cudaErrorNotReady) NSP_CUDA_TRY(ctx, e);

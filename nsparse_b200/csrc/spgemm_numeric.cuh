@@ -738,6 +738,8 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
                    const long long *c_rpt64, int *c_col, real *c_val, int row0, int nrows)
 {
     nsp_spgemm_state &sp = ctx->sp;
+    ctx->dma.t_numeric = std::chrono::steady_clock::now();
+    ctx->dma.last_kernel_ms = 0;
     if (!sp.symbolic_done || sp.M != M || sp.K != K || sp.N != N)
         return ctx->fail(-2, "nsp_spgemm_numeric: call nsp_spgemm_symbolic on the same context and shapes first");
     if (nrows < 0) nrows = M - row0;

@@ -419,9 +419,14 @@ def spgemm_kernel_hash_mgpu(a_local: CSR, b: CSR, cuts, n_rows: int, total_ip: i
             finally:
                 peers.clear_fused_targets()
             peers.check_status()
-            # copy-engine gather: the call returns when the last tile was handed over, i.e. when this rank's kernels
-            # are done -- the rank's own compute time, for partition_rows_by_measured
-            peers.last_compute_s = t_own + (time.perf_counter() - t_num)
+            # the rank's own compute time, for the feedback partitions: symbolic phase + numeric call up to the end of
+            # its kernels (the call itself returns when the last tile has been handed to the copy engines / SMs, which
+            # with many peers is most of the transfer)
+            import ctypes as C
+
+            kms = C.c_double(0.0)
+            ctx.check(ctx.lib.nsp_spgemm_peers_stats(ctx.handle, None, None, C.byref(kms)))
+            peers.last_compute_s = t_own + (kms.value * 1e-3 if kms.value > 0 else time.perf_counter() - t_num)
         elif peers.pieces >= 1 and a_local.M > 0:
             # pipeline: piece k+1 is computed while the copy engines carry piece k to the peers
             main = torch.cuda.current_stream(dev)

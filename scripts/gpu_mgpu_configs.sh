@@ -18,9 +18,11 @@ PY
   grep -E "Error|error" gpurun_out/r2_bench_g${N}_$tag.err | tail -3 | cut -c1-300
 }
 if [ "$FULL" = "full" ]; then
-  run c2 --steps 5 --warmup 3 --cpu-seconds 8
+  run c2 --steps 5 --warmup 3 --cpu-seconds 6
   run c4 --config c4 --steps 3 --warmup 2
   run c5 --config c5 --steps 3 --warmup 2
+  # A/B of the SM-store tail of the gather (csrc/peer_dma.cu): copy engines only, same partition model
+  run c2_ce_only --steps 3 --warmup 3 --no-cpu --no-check --gather-sm 0
 else
   run c2 --steps 3 --warmup 3 --cpu-seconds 5
   run c4small --config c4 --scale 19 --ef 32 --steps 2 --warmup 2

@@ -434,7 +434,7 @@ def test_tile_pusher_on_one_gpu(ns, dtype, offset, mode):
         assert int((pcol[:offset] != -7).sum()) == 0 and int((pcol[offset + nnz:] != -7).sum()) == 0
     if mode != "tma":
         n_ce, n_sm = C.c_longlong(-1), C.c_longlong(-1)
-        ctx.check(ctx.lib.nsp_spgemm_peers_stats(ctx.handle, C.byref(n_ce), C.byref(n_sm)))
+        ctx.check(ctx.lib.nsp_spgemm_peers_stats(ctx.handle, C.byref(n_ce), C.byref(n_sm), None))
         assert n_ce.value >= 0 and n_sm.value >= 0 and n_ce.value + n_sm.value > 0
         if mode == "ce_only":
             assert n_sm.value == 0
