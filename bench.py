@@ -399,6 +399,8 @@ def run_ours(args):
         ctx.set_option("gather_tma", 1)
     if args.gather_sm != 1:
         ctx.set_option("gather_sm", args.gather_sm)
+    if args.hash_order:
+        ctx.set_option("hash_order", args.hash_order)
     if not wl["on_device"]:
         b.memcpy(local)                    # B (replicated); A is B for C2
     torch.cuda.synchronize()
@@ -842,6 +844,7 @@ def main():
     ap.add_argument("--push-sms", type=int, default=0, help="N > 1, --gather-tma: SMs of the pusher kernel (0: library default)")
     ap.add_argument("--gather-tma", action="store_true", help="N > 1: the TMA pusher kernel instead of the copy engines")
     ap.add_argument("--ip-partition", action="store_true", help="N > 1: keep the equal-intermediate-products row blocks")
+    ap.add_argument("--hash-order", type=int, default=0, help="measurements: 1 = bitonic sort of the hash tables always, 2 = no shared-memory bucket ordering")
     ap.add_argument("--gather-sm", type=int, default=1, help="N > 1: 1 = tiles left when the kernels end go out by SM stores next to the copy engines, 0 = copy engines only, 2 = SM stores only")
     ap.add_argument("--out-gbs", type=float, default=400.0, help="N > 1: outbound GB/s per GPU (copy engines, while the kernels run) assumed by the row partition")
     ap.add_argument("--tail-gbs", type=float, default=650.0, help="N > 1: outbound GB/s per GPU once the kernels have ended (copy engines + SM stores) assumed by the row partition")

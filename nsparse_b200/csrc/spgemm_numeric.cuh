@@ -140,6 +140,14 @@ num_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
             // cursor, and the keys that share a bucket are ranked among themselves by counting.  Rows whose columns
             // cluster into one bucket (more than kMaxBucket keys) fall back to the bitonic sort.
             constexpr int kMaxBucket = 768;     // beyond this the O(bucket^2) ranking costs more than the bitonic sort
+            // Buckets of at most kSmallBucket keys (columns spread evenly: B with scattered columns, configs C4 / C5)
+            // are ordered WITHOUT leaving shared memory: every thread takes the keys of its <= 16 table slots into
+            // registers, the key table is then free and receives, at the bucket cursors, one word per entry --
+            // (column bits below the bucket, table slot of the value) -- one thread orders the few words of a bucket
+            // and writes the bucket's entries to C, neighbouring threads neighbouring positions.  (Scattering the
+            // entries to C and ranking them there, the path below, costs four random L2 transactions per entry:
+            // 238 ms instead of the bitonic sort's 99 ms on C5's 5.3e8 entries per GPU, profiles/r2_bench_c5_gpus8*.json.)
+            constexpr int kSmallBucket = 24;
             int nb = tsize >> 1;
             if (nb > nb_max) nb = nb_max;
             int shift = 0;
@@ -167,11 +175,56 @@ num_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
             if ((t & 31) == 0 && mx > 0) atomicMax(&s_maxb[g], mx);
             const int inc = group_inclusive_scan<GROUP>(sum, t, s_flat[g].wtot);
             group_sync<GROUP>();
-            if (s_maxb[g] > kMaxBucket) {
+            const int tbits = 31 - __clz(tsize);
+            const int mxb = s_maxb[g];
+            if (sorted == 2 || mxb > kMaxBucket) {
                 bitonic_sort_slots<GROUP, real>(keys, vals, tsize, t);
                 for (int i = t; i < nnz; i += GROUP) {
                     c_col[off + i] = keys[i];
                     c_val[off + i] = vals[i];
+                }
+            } else if (sorted != 3 && mxb <= kSmallBucket && shift + tbits <= 32 && tsize <= 16 * GROUP) {
+                int run = inc - sum;
+                if (b0 < nb)
+                    for (int k = 0; k < per; ++k) {
+                        const int c = cnt[b0 + k];
+                        cnt[b0 + k] = run;          // cursor of the bucket
+                        run += c;
+                    }
+                int rk[16];                         // tmax / GROUP = 16 slots per thread in every class
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int i = t + j * GROUP;
+                    rk[j] = i < tsize ? keys[i] : kEmptyKey;
+                }
+                group_sync<GROUP>();                // cursors complete, every key is in a register
+                const unsigned lowmask = shift >= 32 ? 0xffffffffu : ((1u << shift) - 1u);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (rk[j] != kEmptyKey) {
+                        const int pos = atomicAdd(&cnt[(unsigned)rk[j] >> shift], 1);
+                        keys[pos] = (int)((((unsigned)rk[j] & lowmask) << tbits) | (unsigned)(t + j * GROUP));
+                    }
+                }
+                group_sync<GROUP>();
+                // cnt[b] is now the END of bucket b
+                for (int b = t; b < nb; b += GROUP) {
+                    const int s0 = b > 0 ? cnt[b - 1] : 0;
+                    const int e0 = cnt[b];
+                    for (int q = s0 + 1; q < e0; ++q) {
+                        const unsigned w = (unsigned)keys[q];
+                        int r = q - 1;
+                        while (r >= s0 && (unsigned)keys[r] > w) {
+                            keys[r + 1] = keys[r];
+                            --r;
+                        }
+                        keys[r + 1] = (int)w;
+                    }
+                    for (int q = s0; q < e0; ++q) {
+                        const unsigned w = (unsigned)keys[q];
+                        c_col[off + q] = (int)(((unsigned)b << shift) | (w >> tbits));
+                        c_val[off + q] = vals[w & mask];
+                    }
                 }
             } else {
                 int run = inc - sum;
@@ -681,8 +734,11 @@ static int launch_num_hash(nsp_context *ctx, const char *name, int grid, const i
     while (nb_max > 16 && table + (size_t)nb_max * sizeof(int) * NG > limit) nb_max >>= 1;
     const size_t smem = table + (size_t)nb_max * sizeof(int) * NG;
     NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // 0: unsorted rows; 1: buckets (in shared memory where they are small, through C otherwise, bitonic sort when the
+    // columns cluster); 2 / 3 (option "hash_order" 1 / 2, measurements): bitonic sort always / no shared-memory buckets
+    const int order = ctx->opt_unsorted ? 0 : (ctx->opt_hash_order == 1 ? 2 : (ctx->opt_hash_order == 2 ? 3 : 1));
     num_prof_class(ctx, name, bin_lo, bin_hi);
-    kern<<<grid, BS, smem, ctx->stream>>>(NSP_NUM_ARGS, bin_lo, bin_hi, queue, tmax, ctx->opt_unsorted ? 0 : 1, nb_max, n_cols,
+    kern<<<grid, BS, smem, ctx->stream>>>(NSP_NUM_ARGS, bin_lo, bin_hi, queue, tmax, order, nb_max, n_cols,
                                           ctx->peer_out);
     ctx->prof_end();
     ctx->launches += 1;

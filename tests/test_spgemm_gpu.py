@@ -484,3 +484,36 @@ def test_flat_traversal_of_the_heavy_kernels(ns, dtype, opts):
     got = c.to_host()
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
     ctx.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("hash_order", [0, 1, 2])
+def test_hash_row_ordering_paths(ns, dtype, hash_order):
+    """The three ways a hash-class row is brought into column order -- buckets ordered inside shared memory (evenly
+    spread columns, the default there), buckets ranked through C (hash_order = 2), bitonic sort of the table
+    (hash_order = 1) -- on a product with evenly spread columns over a WIDE C (2^22 columns: every class of the hash
+    ladder, tables of 32 .. 16384 slots) and on R-MAT A^2 (clustered columns).  Bit-exact against the oracle."""
+    from nsparse_b200 import gen
+
+    ctx = ns.Context(0)
+    ctx.set_option("hash_order", hash_order)
+    n = 1 << 22
+    a = gen.powerlaw_csr(3000, mean_nnz=48, max_row=2000, seed=5, dtype=dtype, values="ones")
+    a = type(a)(a.M, n, a.rpt, (a.col.astype(np.int64) * (n // 3000)).astype(np.int32), a.val, "wide_rows")
+    b = gen.er_csr(n, n, 4, seed=6, dtype=dtype, values="ones")
+    a.memcpy()
+    b.memcpy()
+    c = ns.spgemm_kernel_hash(a, b, ctx)
+    ctx.sync()
+    got = c.to_host()
+    want = oracle.spgemm(a.rpt, a.col, a.val, b.rpt, b.col, b.val, acc_double=True, n_cols=n)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+    assert int(np.diff(want[0]).max()) > 4096, "no row reached the 1024-thread class"
+    r = gen.rmat_csr(12, 16, seed=8, dtype=dtype, values="small_int")
+    r.memcpy()
+    c = ns.spgemm_kernel_hash(r, r, ctx)
+    ctx.sync()
+    got = c.to_host()
+    want = oracle.spgemm(r.rpt, r.col, r.val, r.rpt, r.col, r.val, acc_double=True)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+    ctx.close()
