@@ -893,13 +893,15 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
         const long long a_entries = sp.a_nnz;
         const int mode = !sp.b_sorted ? 0 : (use_seg ? 2 : 1);
         // flat traversal when the B rows of the class are short (spgemm_device.cuh run_flat): products per entry of A
-        // below 48 on average
+        // below 48 on average, and at most 4 windows (every pass touches every product: with the 8 / 32 windows of the
+        // full-size configs C4 / C5 it was 1.7-1.9x slower than the searched sub-ranges,
+        // profiles/r2_ab_flat_traversal_windows.txt)
         long long cls_ip = 0, cls_len = 0;
         for (int b = bm_bin; b < kNumBins; ++b) {
             cls_ip += (long long)sp.h_binsum[kSumIp + b];
             cls_len += (long long)sp.h_binsum[kSumLen + b];
         }
-        const int flat = (mode != 0 && cls_len > 0 && cls_ip < 48 * cls_len && !ctx->opt_no_flat) || (mode != 0 && ctx->opt_no_flat < 0);
+        const int flat = (mode != 0 && cls_len > 0 && cls_ip < 48 * cls_len && nwin_host <= 4 && !ctx->opt_no_flat) || (mode != 0 && ctx->opt_no_flat < 0);
         // [multi][peers][mode][flat]
         using kern_t = void (*)(const int *, const int *, const real *, const int *, const int *, const real *, const long long *,
                                 int *, real *, const int *, int *, int, int, int, int, int, int, int, int, long long *,
