@@ -893,8 +893,8 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
         const long long a_entries = sp.a_nnz;
         const int mode = !sp.b_sorted ? 0 : (use_seg ? 2 : 1);
         // flat traversal when the B rows of the class are short (spgemm_device.cuh run_flat): products per entry of A
-        // below 48 on average, and at most 4 windows (every pass touches every product: with the 8 / 32 windows of the
-        // full-size configs C4 / C5 it was 1.7-1.9x slower than the searched sub-ranges,
+        // below 48 on average, and at most 4 windows (every pass touches every product: with the 16 / 32 windows of the
+        // full-size configs C4 / C5 it was 1.6-2.2x slower than the searched sub-ranges,
         // profiles/r2_ab_flat_traversal_windows.txt)
         long long cls_ip = 0, cls_len = 0;
         for (int b = bm_bin; b < kNumBins; ++b) {

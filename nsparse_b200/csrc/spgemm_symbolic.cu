@@ -272,9 +272,10 @@ int spgemm_symbolic(nsp_context *ctx, int M, int K, int N, const int *a_rpt, con
                 cls_ip += (long long)sp.h_binsum[kSumIp + b];
                 cls_len += (long long)sp.h_binsum[kSumLen + b];
             }
-            // (flat traversal: every pass touches every product, so only with few windows -- measured on the full-size configs
-            // C4 / C5, 8-32 windows: 1.7-1.9x slower than the searched sub-ranges, profiles/r2_ab_flat_traversal_windows.txt)
-            const bool flat = sp.b_sorted && ((cls_len > 0 && cls_ip < 48 * cls_len && nwin_host <= 4 && !ctx->opt_no_flat) || ctx->opt_no_flat < 0);
+            // (flat traversal: every pass touches every product, so only with few windows -- measured on the full-size
+            // configs, profiles/r2_ab_flat_traversal_windows.txt: C4, 8 windows, 54.9 ms flat / 65.0 ms searched sub-ranges;
+            // C5, 16 windows, 157.9 / 81.4 ms)
+            const bool flat = sp.b_sorted && ((cls_len > 0 && cls_ip < 48 * cls_len && nwin_host <= 8 && !ctx->opt_no_flat) || ctx->opt_no_flat < 0);
             auto kern = !sp.b_sorted ? sym_bitmap_kernel<1024, false, false>
                                      : (flat ? sym_bitmap_kernel<1024, true, true> : sym_bitmap_kernel<1024, true, false>);
             const int b_vec_end = ((reinterpret_cast<uintptr_t>(b_col) & 15u) != 0 || ctx->opt_no_vec)
