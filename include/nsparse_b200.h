@@ -51,9 +51,12 @@ int nsp_sync(nsp_context *ctx);
  * products / entries take the bitmap kernels), "sym_window_shift" / "num_window_shift" (log2 of the bitmap window),
  * "num_cap" (upper limit of the accumulator chunk), "sort" (0: the numeric
  * phase may leave the columns of a row unsorted -- SpGEMM_Hash_Numeric<sort = false> of cuda-cpp/inc/HashSpGEMM_volta.hpp:
- * 1018-1031; the hash classes then skip their per-row sort, the bitmap class is sorted by construction), "push_sms",
- * "no_seg", "no_vec" (no 128-bit loads of B.col), "no_fork" (long rows on
- * the main stream), "profile", "debug", "phase_timing" */
+ * 1018-1031; the hash classes then skip their per-row sort, the bitmap class is sorted by construction),
+ * "hash_order" (how a hash-class row is ordered: 0 buckets, 1 bitonic sort always, 2 no shared-memory buckets),
+ * "no_seg", "no_flat" (1: never the flat traversal of short B rows, -1: always), "no_vec" (no 128-bit loads of
+ * B.col), "no_fork" (long rows on the main stream), "gather_sm", "gather_tma", "push_sms", "dma_tile_log" (multi-GPU,
+ * see nsp_spgemm_set_peers), "profile", "debug", "phase_timing".  NSP_OPTIONS="name=value,..." in the environment
+ * sets them at nsp_create. */
 int nsp_set_option(nsp_context *ctx, const char *name, long long value);
 /* With option "profile" = 1 every row-class kernel launch is bracketed by CUDA events on the
  * context's stream.  nsp_profile_dump syncs, writes one line per launch
