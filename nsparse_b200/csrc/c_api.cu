@@ -117,6 +117,7 @@ int nsp_set_option(nsp_context *ctx, const char *name, long long value)
     else if (!strcmp(name, "dma_tile_log")) ctx->opt_dma_tile_log = value;
     else if (!strcmp(name, "gather_sm")) ctx->opt_gather_sm = value;
     else if (!strcmp(name, "hash_order")) ctx->opt_hash_order = value;
+    else if (!strcmp(name, "no_ranges")) ctx->opt_no_ranges = value;
     else if (!strcmp(name, "sort")) ctx->opt_unsorted = value == 0;
     else if (!strcmp(name, "phase_timing")) {
         // value 1: start accumulating; value 2: print the totals (cycles summed over CTAs) and reset

@@ -136,6 +136,7 @@ struct nsp_context {
     nsp_dma_push dma;
     long long opt_gather_tma = 0;        // 1: the TMA pusher kernel (peer_push.cu) instead of the copy engines
     long long opt_dma_tile_log = 0;      // > 0: log2 of the copy-engine tile (tests)
+    long long opt_no_ranges = 0;         // 1: never num_hash_ranges_kernel (wide C, short B rows); -1: whenever it can run
     long long opt_hash_order = 0;        // 1: bitonic table sort always; 2: no shared-memory bucket ordering (measurements)
     long long opt_gather_sm = 1;         // 1: tiles still unsent when the kernels end leave through SM stores next to
                                          // the copy engines; 0: copy engines only; 2: SM stores only (tests)

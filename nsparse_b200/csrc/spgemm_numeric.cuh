@@ -281,6 +281,206 @@ num_hash_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
     }
 }
 
+// ---- wide C, short B rows: hash passes over COLUMN RANGES -----------------------------------------
+// The rows above the hash ladder (more than 8192 entries) of a product whose C is many bitmap windows wide and whose
+// B rows are short (configs C4 / C5: B with 4 entries per row, C 2^23 / 2^24 columns wide).  The bitmap kernel
+// walks all entries of the row of A once per 2^19-column window -- 16 / 32 passes whatever the row holds
+// (profiles/r2_ab_flat_traversal_windows.txt).  Here the number of passes follows the OUTPUT instead: one pass counts the row's
+// products per column bin (2048 bins of <= 8192 columns), the bins are grouped into ranges of at most 3/4 * tmax
+// products -- so a range can never overflow the table; a single bin cannot either, it has fewer columns than that --
+// and every range is one hash pass over the row's products (those outside the range are skipped), ordered by the
+// bucket scheme of num_hash_kernel and appended to the row.  Ranges ascend, so the row comes out sorted.
+// This is the bounded table north_star asks for where the reference falls back to global memory
+// (kernel_spgemm_hash_d.cu:929-1033): shared memory, bounded by construction, no retry.
+constexpr int kRangeBins = 2048;
+
+template <typename real>
+__global__ void __launch_bounds__(1024, 1)
+num_hash_ranges_kernel(const int *__restrict__ a_rpt, const int *__restrict__ a_col,
+                       const real *__restrict__ a_val, const int *__restrict__ b_rpt,
+                       const int *__restrict__ b_col, const real *__restrict__ b_val,
+                       const long long *__restrict__ c_rpt, int *__restrict__ c_col, real *__restrict__ c_val,
+                       const int *__restrict__ row_perm, int *__restrict__ bins, int bin_lo, int bin_hi,
+                       int queue, int tmax, int nb_max, int n_cols, int bshift, const __grid_constant__ PeerOut peer)
+{
+    constexpr int GROUP = 1024;
+    constexpr int kSmallBucket = 24;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ FlatScratch<GROUP, real> s_flat;
+    __shared__ int s_row, s_maxb, s_tot;
+    __shared__ int s_rng[3];
+    real *vals = reinterpret_cast<real *>(smem_raw);
+    int *keys = reinterpret_cast<int *>(smem_raw + sizeof(real) * (size_t)tmax);
+    int *cnt = keys + tmax;
+    int *hist = cnt + nb_max;              // products per column bin, then their inclusive prefix
+    const int t = threadIdx.x;
+    const int cap = tmax / 4 * 3;
+    int lo, hi;
+    class_range(bins, bin_lo, bin_hi, lo, hi);
+    const int n = hi - lo;
+    while (true) {
+        __syncthreads();                   // (s_row of the previous row has been read by everyone)
+        if (t == 0) s_row = atomicAdd(&bins[kBinQueue + queue], 1);
+        __syncthreads();
+        const int r = s_row;
+        if (r >= n) break;
+        const int rid = row_perm[lo + r];
+        const long long off = c_rpt[rid];
+        const int nnz = (int)(c_rpt[rid + 1] - off);
+        const int a_lo = a_rpt[rid], a_hi = a_rpt[rid + 1];
+        for (int i = t; i < kRangeBins; i += GROUP) hist[i] = 0;
+        __syncthreads();
+        for_each_product<GROUP, false, real>(t, a_lo, a_hi, a_col, a_val, b_rpt, b_col, b_val, s_flat,
+                                             [&](int c, real) { atomicAdd(&hist[(unsigned)c >> bshift], 1); });
+        __syncthreads();
+        {
+            // inclusive prefix over the bins: two consecutive bins per thread
+            const int v0 = hist[2 * t], v1 = hist[2 * t + 1];
+            const int inc = group_inclusive_scan<GROUP>(v0 + v1, t, s_flat.wtot);
+            hist[2 * t] = inc - v1;
+            hist[2 * t + 1] = inc;
+        }
+        __syncthreads();
+        const int row_products = hist[kRangeBins - 1];
+        int written = 0;
+        int bin = 0;                       // first bin not yet processed (uniform)
+        while (true) {
+            if (t == 0) {
+                const int base = bin > 0 ? hist[bin - 1] : 0;
+                if (base >= row_products) {
+                    s_rng[0] = -1;
+                } else {
+                    // first bin with products, then as many bins as fit `cap` products (at least one)
+                    int l = bin, h = kRangeBins - 1;
+                    while (l < h) {
+                        const int m = (l + h) >> 1;
+                        if (hist[m] > base) h = m; else l = m + 1;
+                    }
+                    const int first = l;
+                    l = first;
+                    h = kRangeBins;
+                    while (l < h) {
+                        const int m = (l + h) >> 1;
+                        if (hist[m] - base > cap) h = m; else l = m + 1;
+                    }
+                    const int end = l > first + 1 ? l : first + 1;
+                    s_rng[0] = first;
+                    s_rng[1] = end;
+                    s_rng[2] = hist[end - 1] - base;
+                }
+            }
+            __syncthreads();
+            const int rb0 = s_rng[0];
+            if (rb0 < 0) break;
+            const int rb1 = s_rng[1];
+            const int prod = s_rng[2];
+            bin = rb1;
+            const int c_lo = rb0 << bshift;
+            const long long c_hi = (long long)rb1 << bshift;
+            const int width = (int)((c_hi < (long long)n_cols ? c_hi : (long long)n_cols) - c_lo);
+            const int tsize = table_size_for(prod < width ? prod : width, tmax);
+            const unsigned mask = (unsigned)tsize - 1u;
+            for (int i = t; i < tsize; i += GROUP) {
+                keys[i] = kEmptyKey;
+                vals[i] = real(0);
+            }
+            __syncthreads();               // (also: everyone has read s_rng)
+            const unsigned uw = (unsigned)width;
+            for_each_product<GROUP, true, real>(t, a_lo, a_hi, a_col, a_val, b_rpt, b_col, b_val, s_flat,
+                                                [&](int c, real v) {
+                                                    if ((unsigned)(c - c_lo) < uw) hash_accumulate(keys, vals, mask, c, v);
+                                                });
+            __syncthreads();
+            // order the range: buckets over [c_lo, c_lo + width), see num_hash_kernel
+            int nb = tsize >> 1;
+            if (nb > nb_max) nb = nb_max;
+            int shift = 0;
+            while (((unsigned)(width - 1) >> shift) >= (unsigned)nb) ++shift;
+            for (int i = t; i < nb; i += GROUP) cnt[i] = 0;
+            if (t == 0) s_maxb = 0;
+            __syncthreads();
+            for (int i = t; i < tsize; i += GROUP) {
+                const int key = keys[i];
+                if (key != kEmptyKey) atomicAdd(&cnt[(unsigned)(key - c_lo) >> shift], 1);
+            }
+            __syncthreads();
+            const int per = nb >= GROUP ? nb / GROUP : 1;
+            const int b0 = t * per;
+            int sum = 0, mx = 0;
+            if (b0 < nb)
+                for (int k = 0; k < per; ++k) {
+                    const int c = cnt[b0 + k];
+                    sum += c;
+                    mx = c > mx ? c : mx;
+                }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if ((t & 31) == 0 && mx > 0) atomicMax(&s_maxb, mx);
+            const int inc = group_inclusive_scan<GROUP>(sum, t, s_flat.wtot);
+            if (t == GROUP - 1) s_tot = inc;
+            __syncthreads();
+            const int total = s_tot;       // entries of the range
+            const int tbits = 31 - __clz(tsize);
+            const long long out = off + written;
+            if (s_maxb > kSmallBucket || shift + tbits > 32) {
+                // clustered columns: bitonic sort of the table (free slots sort behind the keys)
+                bitonic_sort_slots<GROUP, real>(keys, vals, tsize, t);
+                for (int i = t; i < total; i += GROUP) {
+                    c_col[out + i] = keys[i];
+                    c_val[out + i] = vals[i];
+                }
+            } else {
+                int run = inc - sum;
+                if (b0 < nb)
+                    for (int k = 0; k < per; ++k) {
+                        const int c = cnt[b0 + k];
+                        cnt[b0 + k] = run;          // cursor of the bucket
+                        run += c;
+                    }
+                int rk[16];                         // tmax / GROUP <= 16 slots per thread
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int i = t + j * GROUP;
+                    rk[j] = i < tsize ? keys[i] : kEmptyKey;
+                }
+                __syncthreads();                    // cursors complete, every key is in a register
+                const unsigned lowmask = (1u << shift) - 1u;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (rk[j] != kEmptyKey) {
+                        const unsigned rel = (unsigned)(rk[j] - c_lo);
+                        const int pos = atomicAdd(&cnt[rel >> shift], 1);
+                        keys[pos] = (int)(((rel & lowmask) << tbits) | (unsigned)(t + j * GROUP));
+                    }
+                }
+                __syncthreads();
+                // cnt[b] is now the END of bucket b
+                for (int b = t; b < nb; b += GROUP) {
+                    const int s0 = b > 0 ? cnt[b - 1] : 0;
+                    const int e0 = cnt[b];
+                    for (int q = s0 + 1; q < e0; ++q) {
+                        const unsigned w = (unsigned)keys[q];
+                        int rr = q - 1;
+                        while (rr >= s0 && (unsigned)keys[rr] > w) {
+                            keys[rr + 1] = keys[rr];
+                            --rr;
+                        }
+                        keys[rr + 1] = (int)w;
+                    }
+                    for (int q = s0; q < e0; ++q) {
+                        const unsigned w = (unsigned)keys[q];
+                        c_col[out + q] = c_lo + (int)(((unsigned)b << shift) | (w >> tbits));
+                        c_val[out + q] = vals[w & mask];
+                    }
+                }
+            }
+            written += total;
+            __syncthreads();               // the table is cleared for the next range
+        }
+        if (peer.n > 0 && t == 0) tiles_done(peer, off, nnz);
+    }
+}
+
 // ---- bitmap + rank + shared-memory accumulator class ---------------------------------------------
 // A row of C is produced in ascending column WINDOWS of W = 2^wshift columns and, inside a window,
 // in CHUNKS of at most `cap` output entries:
@@ -760,6 +960,7 @@ static int preload_numeric_kernels(nsp_context *ctx)
     NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_hash_kernel<real, 32, 256>));
     NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_hash_kernel<real, 256, 256>));
     NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_hash_kernel<real, 1024, 1024>));
+    NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_hash_ranges_kernel<real>));
     NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 0, true, false, false>));
     NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 1, true, false, false>));
     NSP_CUDA_TRY(ctx, cudaFuncGetAttributes(&at, num_bitmap_kernel<real, 1024, 2, true, false, false>));
@@ -984,13 +1185,47 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
         }
         return 0;
     };
+    // Wide C with short B rows (C4 / C5 at full size): the rows above the hash ladder take hash passes over column
+    // ranges (num_hash_ranges_kernel) instead of the bitmap windows.  Needs at most 8192 columns per bin.
+    int rbshift = 0;
+    while (((long long)N - 1) >> rbshift >= (long long)kRangeBins) ++rbshift;
+    bool use_ranges = false;
+    {
+        long long cls_ip = 0, cls_len = 0;
+        for (int b = bm_bin; b < kNumBins; ++b) {
+            cls_ip += (long long)sp.h_binsum[kSumIp + b];
+            cls_len += (long long)sp.h_binsum[kSumLen + b];
+        }
+        use_ranges = rbshift <= 13 && ((nwin_host > 4 && cls_len > 0 && cls_ip < 48 * cls_len && !ctx->opt_no_ranges) || ctx->opt_no_ranges < 0);
+    }
+    auto launch_ranges = [&]() -> int {
+        const long long rows = num_rows_in(sp, bm_bin, kNumBins - 1);
+        if (rows == 0) return 0;
+        const int tmax = 16384;
+        const size_t table = (size_t)tmax * (sizeof(real) + sizeof(int));
+        const size_t limit = (size_t)ctx->max_smem_optin - (sizeof(FlatScratch<1024, real>) + 256) - sizeof(int) * kRangeBins;
+        int nb_max = tmax / 2;
+        while (nb_max > 16 && table + (size_t)nb_max * sizeof(int) > limit) nb_max >>= 1;
+        const size_t smem = table + (size_t)nb_max * sizeof(int) + sizeof(int) * kRangeBins;
+        auto kern = num_hash_ranges_kernel<real>;
+        NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = num_imin(rows, (long long)(sms - push_sms));
+        num_prof_class(ctx, "num_hash_ranges", bm_bin, kNumBins - 1);
+        kern<<<grid, 1024, smem, ctx->stream>>>(NSP_NUM_ARGS, bm_bin, kNumBins - 1, 4, tmax, nb_max, N, rbshift, ctx->peer_out);
+        ctx->prof_end();
+        ctx->launches += 1;
+        NSP_CUDA_TRY(ctx, cudaGetLastError());
+        return 0;
+    };
     // One GPU: heaviest class first (the long rows on their side stream, then the main launch), the light classes fill
     // the tail.  Multi-GPU: a tile of C can leave for the peers once ALL rows that overlap it are done, so the long
     // rows start at once (nothing is queued ahead of them: if they had to wait for the light classes next to the main
     // launch, whichever of the two the hardware released first took every SM -- measured: the long rows then ran last
     // and no tile finished before the end), the (short) light classes follow and the main launch, which completes
     // tiles steadily, comes last.
-    if (peers) {
+    if (use_ranges) {
+        if (peers ? (launch_light() != 0 || launch_ranges() != 0) : (launch_ranges() != 0 || launch_light() != 0)) return -1;
+    } else if (peers) {
         if (launch_bitmap(1) != 0 || launch_light() != 0 || launch_bitmap(0) != 0) return -1;
     } else {
         if (launch_bitmap(1) != 0 || launch_bitmap(0) != 0 || launch_light() != 0) return -1;

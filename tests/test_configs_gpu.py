@@ -64,6 +64,21 @@ def test_c5_reduced_powerlaw_overflow_rows_fp64(ns):
     ctx.close()
 
 
+def test_c5_reduced_wide_c_hash_ranges_fp64(ns):
+    """The same power-law A times a B that makes C 2^23 columns wide (16 numeric bitmap windows): with 4-entry B rows
+    the rows above the hash ladder -- also the 64 K-entry row, 262 144 products in 22 column ranges -- go through
+    num_hash_ranges_kernel (the default there)."""
+    from nsparse_b200 import gen
+
+    n = 1 << 17
+    a = gen.powerlaw_csr(n, mean_nnz=48, max_row=65536, seed=777, dtype=np.float64, values="ones")
+    b = gen.er_csr(n, 1 << 23, 4, seed=54321, dtype=np.float64, values="ones")
+    ctx = ns.Context(0)
+    c = _check(ns, ctx, a, b)
+    assert c.nnz > 3 * a.nnz
+    ctx.close()
+
+
 def test_c2_full_size_properties(ns):
     """Config C2 itself: 2.09e10 intermediate products, 9.7e9 output entries (int64 row pointer)."""
     import torch

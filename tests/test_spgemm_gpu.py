@@ -384,8 +384,8 @@ def test_host_drain_fold(ns, ctx):
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("offset", [0, 12345])
-@pytest.mark.parametrize("mode", ["dma", "dma_small_tiles", "dma_small_tiles_3peers", "ce_only", "sm_only", "sm_only_small_tiles",
-                                  "sm_only_3peers", "tma"])
+@pytest.mark.parametrize("mode", ["dma", "dma_small_tiles", "dma_small_tiles_3peers", "dma_small_tiles_ranges", "ce_only", "sm_only",
+                                  "sm_only_small_tiles", "sm_only_3peers", "tma"])
 def test_tile_pusher_on_one_gpu(ns, dtype, offset, mode):
     """The multi-GPU allgatherv path (tile counters in every numeric kernel, then either the copy engines driven by
     the polling host thread plus SM stores for what is left when the kernels end, csrc/peer_dma.cu -- each of the two
@@ -405,6 +405,8 @@ def test_tile_pusher_on_one_gpu(ns, dtype, offset, mode):
         ctx.set_option("dma_tile_log", 12)
     if mode == "ce_only":
         ctx.set_option("gather_sm", 0)
+    if mode.endswith("ranges"):
+        ctx.set_option("no_ranges", -1)      # the heavy rows through num_hash_ranges_kernel (it counts tiles too)
     if mode.startswith("sm_only"):
         ctx.set_option("gather_sm", 2)
     a = gen.rmat_csr(13, 16, seed=4, dtype=dtype, values="small_int")
@@ -515,5 +517,44 @@ def test_hash_row_ordering_paths(ns, dtype, hash_order):
     ctx.sync()
     got = c.to_host()
     want = oracle.spgemm(r.rpt, r.col, r.val, r.rpt, r.col, r.val, acc_double=True)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+    ctx.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_wide_product_hash_ranges(ns, dtype):
+    """num_hash_ranges_kernel: rows above the hash ladder (more than 8192 entries) of a product with a WIDE C (2^22
+    columns: 8 bitmap windows) and 4-entry B rows take hash passes over column ranges instead of the bitmap windows --
+    rows of one range, of several ranges, and (forced with no_ranges = -1) R-MAT A^2, whose columns cluster so that
+    ranges are single bins and the bitonic fallback orders them.  Bit-exact against the oracle, and against the bitmap
+    kernels (no_ranges = 1) on the same input."""
+    from nsparse_b200 import gen
+
+    n = 1 << 22
+    a = gen.powerlaw_csr(3000, mean_nnz=48, max_row=3000, seed=11, dtype=dtype, values="ones")
+    # (rows of up to 3000 entries times 12-entry B rows: up to 36000 outputs, three ranges)
+    a = type(a)(a.M, n, a.rpt, (a.col.astype(np.int64) * (n // 3000)).astype(np.int32), a.val, "wide_rows")
+    b = gen.er_csr(n, n, 12, seed=12, dtype=dtype, values="ones")
+    a.memcpy()
+    b.memcpy()
+    want = oracle.spgemm(a.rpt, a.col, a.val, b.rpt, b.col, b.val, acc_double=True, n_cols=n)
+    per_row = np.diff(want[0])
+    assert int(per_row.max()) > 2 * 12288 and int(((per_row > 8192) & (per_row <= 12288)).sum()) > 0
+    for no_ranges in (0, 1):
+        ctx = ns.Context(0)
+        ctx.set_option("no_ranges", no_ranges)
+        c = ns.spgemm_kernel_hash(a, b, ctx)
+        ctx.sync()
+        got = c.to_host()
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+        ctx.close()
+    r = gen.rmat_csr(13, 16, seed=3, dtype=dtype, values="small_int")
+    r.memcpy()
+    want = oracle.spgemm(r.rpt, r.col, r.val, r.rpt, r.col, r.val, acc_double=True)
+    ctx = ns.Context(0)
+    ctx.set_option("no_ranges", -1)
+    c = ns.spgemm_kernel_hash(r, r, ctx)
+    ctx.sync()
+    got = c.to_host()
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
     ctx.close()
