@@ -1054,6 +1054,7 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
         if (bm_bin < 1) bm_bin = 1;
         if (bm_bin > 10) bm_bin = 10;
     }
+    int bm_lo = bm_bin;      // first bin of the bitmap kernels (above bm_bin when num_hash_ranges_kernel takes the lower bins)
     const int sms = ctx->sm_count;
     // the side-stream launch of the long rows is joined on EVERY exit path, also the early error returns of the
     // launches below (the aux kernel reads d_bins / d_row_perm, which the next call rewrites)
@@ -1085,12 +1086,12 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
     const int push_sms = ctx->push_active ? ctx->push_ctas : 0;
 
     auto launch_bitmap = [&](int multi) -> int {
-        if (num_rows_in(sp, bm_bin, kNumBins - 1) == 0) return 0;
+        if (num_rows_in(sp, bm_lo, kNumBins - 1) == 0) return 0;
         if (multi && !sp.has_multi_slab) return 0;
         if (cap < 128 || ((1ll << wshift) + cap - 1) / cap > kMaxChunks)
             return ctx->fail(-4, "nsp_spgemm_numeric: shared memory too small for the bitmap kernel");
         const size_t smem = fixed + (size_t)cap * (sizeof(real) + sizeof(int));
-        const int grid = num_imin(num_rows_in(sp, bm_bin, kNumBins - 1), (long long)(sms - push_sms));
+        const int grid = num_imin(num_rows_in(sp, bm_lo, kNumBins - 1), (long long)(sms - push_sms));
         const long long a_entries = sp.a_nnz;
         const int mode = !sp.b_sorted ? 0 : (use_seg ? 2 : 1);
         // flat traversal when the B rows of the class are short (spgemm_device.cuh run_flat): products per entry of A
@@ -1098,7 +1099,7 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
         // full-size configs C4 / C5 it was 1.6-2.2x slower than the searched sub-ranges,
         // profiles/r2_ab_flat_traversal_windows.txt)
         long long cls_ip = 0, cls_len = 0;
-        for (int b = bm_bin; b < kNumBins; ++b) {
+        for (int b = bm_lo; b < kNumBins; ++b) {
             cls_ip += (long long)sp.h_binsum[kSumIp + b];
             cls_len += (long long)sp.h_binsum[kSumLen + b];
         }
@@ -1134,8 +1135,8 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
             st = ctx->aux_stream;
         }
         ctx->prof_on_aux = st != ctx->stream;
-        num_prof_class(ctx, multi ? "num_bitmap_long" : "num_bitmap", bm_bin, kNumBins - 1);
-        kern<<<grid, 1024, smem, st>>>(NSP_NUM_ARGS, bm_bin, kNumBins - 1, multi ? 5 : 4, N, wshift, cap,
+        num_prof_class(ctx, multi ? "num_bitmap_long" : "num_bitmap", bm_lo, kNumBins - 1);
+        kern<<<grid, 1024, smem, st>>>(NSP_NUM_ARGS, bm_lo, kNumBins - 1, multi ? 5 : 4, N, wshift, cap,
                                        b_vec_end_of(ctx, b_col), (int)ctx->opt_debug,
                                        ctx->opt_phase_timing ? ctx->phase_cycles() : nullptr, use_seg ? ctx->d_seg : nullptr,
                                        a_entries, ctx->peer_out);
@@ -1198,8 +1199,19 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
         }
         use_ranges = rbshift <= 13 && ((nwin_host > 4 && cls_len > 0 && cls_ip < 48 * cls_len && !ctx->opt_no_ranges) || ctx->opt_no_ranges < 0);
     }
+    // A row of P products costs P / 12288 + 1 walks over its products there and nwin walks over its entries of A in the
+    // bitmap kernel: the bins below nwin * 12288 entries go to the ranges, the rows above stay with the bitmap kernels
+    // (C4: the hub rows of the R-MAT factor, up to millions of products).  no_ranges = -1 (tests): everything.
+    int rg_hi = kNumBins - 1;
+    if (use_ranges && ctx->opt_no_ranges >= 0) {
+        const long long lim = nwin_host * 12288ll;
+        rg_hi = log_bin((int)(lim < 0x7fffffffll ? lim : 0x7fffffffll), kNumShift) - 1;
+        if (rg_hi > kNumBins - 1) rg_hi = kNumBins - 1;
+        if (rg_hi < bm_bin) use_ranges = false;
+    }
+    bm_lo = use_ranges ? rg_hi + 1 : bm_bin;
     auto launch_ranges = [&]() -> int {
-        const long long rows = num_rows_in(sp, bm_bin, kNumBins - 1);
+        const long long rows = num_rows_in(sp, bm_bin, rg_hi);
         if (rows == 0) return 0;
         const int tmax = 16384;
         const size_t table = (size_t)tmax * (sizeof(real) + sizeof(int));
@@ -1210,8 +1222,8 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
         auto kern = num_hash_ranges_kernel<real>;
         NSP_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = num_imin(rows, (long long)(sms - push_sms));
-        num_prof_class(ctx, "num_hash_ranges", bm_bin, kNumBins - 1);
-        kern<<<grid, 1024, smem, ctx->stream>>>(NSP_NUM_ARGS, bm_bin, kNumBins - 1, 4, tmax, nb_max, N, rbshift, ctx->peer_out);
+        num_prof_class(ctx, "num_hash_ranges", bm_bin, rg_hi);
+        kern<<<grid, 1024, smem, ctx->stream>>>(NSP_NUM_ARGS, bm_bin, rg_hi, 6, tmax, nb_max, N, rbshift, ctx->peer_out);
         ctx->prof_end();
         ctx->launches += 1;
         NSP_CUDA_TRY(ctx, cudaGetLastError());
@@ -1224,7 +1236,9 @@ int spgemm_numeric(nsp_context *ctx, int M, int K, int N, const int *a_rpt, cons
     // and no tile finished before the end), the (short) light classes follow and the main launch, which completes
     // tiles steadily, comes last.
     if (use_ranges) {
-        if (peers ? (launch_light() != 0 || launch_ranges() != 0) : (launch_ranges() != 0 || launch_light() != 0)) return -1;
+        if (peers ? (launch_bitmap(1) != 0 || launch_light() != 0 || launch_ranges() != 0 || launch_bitmap(0) != 0)
+                  : (launch_bitmap(1) != 0 || launch_bitmap(0) != 0 || launch_ranges() != 0 || launch_light() != 0))
+            return -1;
     } else if (peers) {
         if (launch_bitmap(1) != 0 || launch_light() != 0 || launch_bitmap(0) != 0) return -1;
     } else {

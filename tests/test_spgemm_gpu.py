@@ -531,15 +531,17 @@ def test_wide_product_hash_ranges(ns, dtype):
     from nsparse_b200 import gen
 
     n = 1 << 22
-    a = gen.powerlaw_csr(3000, mean_nnz=48, max_row=3000, seed=11, dtype=dtype, values="ones")
-    # (rows of up to 3000 entries times 12-entry B rows: up to 36000 outputs, three ranges)
-    a = type(a)(a.M, n, a.rpt, (a.col.astype(np.int64) * (n // 3000)).astype(np.int32), a.val, "wide_rows")
+    a = gen.powerlaw_csr(8000, mean_nnz=24, max_row=7000, seed=11, dtype=dtype, values="ones")
+    # (rows of up to 7000 entries times 12-entry B rows: up to 84000 outputs; rows of more than 8 windows x 12288
+    # entries stay with the bitmap kernels, the others take one to six ranges)
+    a = type(a)(a.M, n, a.rpt, (a.col.astype(np.int64) * (n // 8000)).astype(np.int32), a.val, "wide_rows")
     b = gen.er_csr(n, n, 12, seed=12, dtype=dtype, values="ones")
     a.memcpy()
     b.memcpy()
     want = oracle.spgemm(a.rpt, a.col, a.val, b.rpt, b.col, b.val, acc_double=True, n_cols=n)
     per_row = np.diff(want[0])
-    assert int(per_row.max()) > 2 * 12288 and int(((per_row > 8192) & (per_row <= 12288)).sum()) > 0
+    assert int(per_row.max()) > 65536 and int(((per_row > 2 * 12288) & (per_row <= 65536)).sum()) > 0
+    assert int(((per_row > 8192) & (per_row <= 12288)).sum()) > 0
     for no_ranges in (0, 1):
         ctx = ns.Context(0)
         ctx.set_option("no_ranges", no_ranges)
