@@ -53,7 +53,8 @@ int nsp_sync(nsp_context *ctx);
  * phase may leave the columns of a row unsorted -- SpGEMM_Hash_Numeric<sort = false> of cuda-cpp/inc/HashSpGEMM_volta.hpp:
  * 1018-1031; the hash classes then skip their per-row sort, the bitmap class is sorted by construction),
  * "hash_order" (how a hash-class row is ordered: 0 buckets, 1 bitonic sort always, 2 no shared-memory buckets),
- * "no_seg", "no_flat" (1: never the flat traversal of short B rows, -1: always), "no_vec" (no 128-bit loads of
+ * "no_seg", "no_flat" (1: never the flat traversal of short B rows, -1: always), "no_ranges" (1: never the
+ * column-range hash kernel for wide products with short B rows, -1: whenever it can run), "no_vec" (no 128-bit loads of
  * B.col), "no_fork" (long rows on the main stream), "gather_sm", "gather_tma", "push_sms", "dma_tile_log" (multi-GPU,
  * see nsp_spgemm_set_peers), "profile", "debug", "phase_timing".  NSP_OPTIONS="name=value,..." in the environment
  * sets them at nsp_create. */
