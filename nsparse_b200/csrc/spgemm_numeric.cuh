@@ -6,14 +6,17 @@
 // output rows sorted by ascending column, numerical zeros kept.  Re-designed for B200:
 //   * tables up to 16384 (key,value) slots (192 KiB in fp64; reference: 4096), sized per row and
 //     never above 3/4 load;
-//   * the whole table is sorted bitonically with the free slots (key 0xffffffff) sinking to the
-//     end, which replaces the global-atomic compaction (:904-912) AND the O(nnz^2) counting sort
-//     (:917-925) with O(n log^2 n) shared-memory work and no global atomics;
+//   * the row is brought into column order by BUCKETS of the column range (count, scan, scatter; small buckets are
+//     ordered inside shared memory, clustered ones ranked by counting, see num_hash_kernel), with a bitonic sort of
+//     the whole table -- free slots (key 0xffffffff) sinking to the end -- as the fallback: this replaces the
+//     global-atomic compaction (:904-912) AND the O(nnz^2) counting sort (:917-925);
 //   * rows above ~2048 entries (reference: each_gl with 2*max_nz global slots PER ROW and an O(nnz^2) sort
 //     in global memory, :929-1027) use a column-window BITMAP + RANK scheme with accumulators in shared
 //     memory: the row's columns are marked in a bitmap, a sweep turns it into ranks, the products are added
 //     at acc[rank] with shared-memory atomics chunk by chunk and written out with coalesced stores; no
 //     table, no compaction, no sort, no workspace (num_bitmap_kernel below);
+//   * where C is many windows wide and the rows of B are short, those rows take hash passes over column ranges
+//     sized by their products instead (num_hash_ranges_kernel below);
 //   * native fp64 atomics everywhere (reference SpMV/SpGEMM fall back to CAS loops on fp64 in global memory).
 #pragma once
 
